@@ -1,0 +1,155 @@
+/*
+ * dpc_b200.h -- C ABI of the B200-native differentiable point-cloud projection.
+ *
+ * The reference (NiteshBharadwaj/pytorch-unsup-pc) has NO native layer: the
+ * path is plain Python/torch (dpc/util/point_cloud_to.py, drc.py,
+ * gauss_kernel.py, quaternion.py).  This header is therefore the boundary a
+ * maintainer binds with ctypes; each entry point names
+ * the reference function(s) (file:line under /root/reference/dpc) it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *    tensors are dense, row-major, fp32 unless stated;
+ *  - the caller owns every buffer (outputs, saved state, workspace); the
+ *    library never allocates, never synchronises the host and keeps no
+ *    mutable global state besides the thread-local error string;
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*) of the
+ *    CURRENT device;
+ *  - return 0 on success, a negative dpc_status otherwise;
+ *    dpc_last_error() describes the last failure on the calling thread;
+ *  - "NULL ok" marks optional arguments.
+ *
+ * Layouts (P projections, N points, grid Vz x V x V, V in {32,64,128}):
+ *   points/tr_pc/g_points  [P,N,3]      quat [P,4]   trans [P,3]
+ *   focal/scale            [P]          grid [P,Vz,V,V]
+ *   mask/depth             [P,V,V]      probs [Vz+1,P,V,V]
+ *   clamp bits             [P,Vz,V,V/32] uint32, bit x%32 of word x/32
+ *   taps                   HOST pointers, odd length <= DPC_MAX_TAPS
+ */
+#ifndef DPC_B200_H
+#define DPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DPC_API __attribute__((visibility("default")))
+#else
+#define DPC_API
+#endif
+
+#define DPC_B200_VERSION 100
+#define DPC_MAX_TAPS 21
+
+typedef enum {
+  DPC_OK = 0,
+  DPC_ERR_ARG = -1,         /* bad shape / NULL / unsupported size  */
+  DPC_ERR_CUDA = -2,        /* CUDA runtime error at launch         */
+  DPC_ERR_WORKSPACE = -3    /* workspace too small                  */
+} dpc_status;
+
+/* Geometry + the config keys the path reads (default_config.yaml:72-83). */
+typedef struct {
+  int32_t P, N;             /* projections, points per cloud                    */
+  int32_t Vz, V;            /* vox_size_z (or vox_size when -1), vox_size       */
+  double camera_distance;   /* cfg.camera_distance                              */
+  double focal_length;      /* cfg.focal_length, used when focal == NULL        */
+  double max_depth;         /* cfg.max_depth                                    */
+  double drc_clip;          /* cfg.drc_logsum_clip_val                          */
+  int32_t drc_logsum;       /* cfg.drc_logsum: 1 = clip + exp(clip) end factors */
+  int32_t flip_y;           /* 1 = apply the Y flips of point_cloud_to.py:239,242 */
+} dpc_params;
+
+/* Flags for dpc_project_fwd / scatter mode. */
+#define DPC_SCATTER_ATOMIC 0
+#define DPC_SCATTER_SORTED 1   /* deterministic sort-then-segment */
+
+DPC_API int dpc_version(void);
+DPC_API const char *dpc_last_error(void);
+
+/* Bytes of workspace the calls below need for this geometry (one buffer is
+ * shared by all of them; 256-byte aligned). */
+DPC_API size_t dpc_workspace_bytes(const dpc_params *p);
+
+/* ---- a1+a2: quaternion.py:110-132 quaternion_rotate +
+ *      point_cloud_to.py:118-178 pc_perspective_transform ------------------ */
+DPC_API int dpc_pose_fwd(const dpc_params *p, const float *points, const float *quat,
+                 const float *trans /*NULL ok*/, const float *focal /*NULL ok*/,
+                 float *tr_pc, void *stream);
+/* Adjoint: g_tr_pc -> g_points [P,N,3], g_quat [P,4], g_trans [P,3] (NULL ok),
+ * g_focal [P] (NULL ok). */
+DPC_API int dpc_pose_bwd(const dpc_params *p, const float *points, const float *quat,
+                 const float *trans, const float *focal, const float *g_tr_pc,
+                 float *g_points, float *g_quat, float *g_trans, float *g_focal,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- a3: point_cloud_to.py:10-87 pointcloud2voxels3d_fast ----------------
+ * Trilinear scatter of already-transformed points.  `grid` is overwritten.
+ * mode DPC_SCATTER_SORTED is bit-exact run to run. */
+DPC_API int dpc_scatter_fwd(const dpc_params *p, const float *tr_pc, float *grid, int mode,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* Adjoint: atomic-free gather of g_grid at the 8 corners -> g_tr_pc. */
+DPC_API int dpc_scatter_bwd(const dpc_params *p, const float *tr_pc, const float *g_grid,
+                    float *g_tr_pc, void *stream);
+
+/* ---- a6: point_cloud_to.py:90-103 smoothen_voxels3d ----------------------
+ * Zero-padded 'same' separable cross-correlation X, Y, Z.  src == dst allowed.
+ * Self-adjoint for symmetric taps, so it is its own backward. */
+DPC_API int dpc_blur3d(const dpc_params *p, const float *src, float *dst,
+               const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+               const float *taps_z_host, int kz, void *stream);
+
+/* ---- a8-a11: drc.py:48-129 drc_projection, :145-160 drc_depth_projection --
+ * voxels [P,Vz,V,V] -> mask [P,V,V], probs [Vz+1,P,V,V] (NULL ok),
+ * depth [P,V,V] (NULL ok).  No blur, no scaling; honours p->flip_y. */
+DPC_API int dpc_drc_fwd(const dpc_params *p, const float *voxels, float *mask, float *depth,
+                float *probs, void *stream);
+DPC_API int dpc_drc_bwd(const dpc_params *p, const float *voxels, const float *g_mask /*NULL ok*/,
+                const float *g_depth /*NULL ok*/, const float *g_probs /*NULL ok*/,
+                float *g_voxels, void *workspace, size_t workspace_bytes, void *stream);
+/* drc.py:152-160 on stored probabilities, and its adjoint. */
+DPC_API int dpc_depth_from_probs_fwd(const dpc_params *p, const float *probs, float *depth, void *stream);
+DPC_API int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, float *g_probs,
+                             void *stream);
+
+/* ---- a12+a13: point_cloud_to.py:191-263 pointcloud_project_fast ----------
+ * The whole path in one call: pose -> scatter -> clamp -> blur XY (in place)
+ * -> blur Z + scale + clip + DRC ray march (+ Y flips).
+ * Saved for backward: grid_xy [P,Vz,V,V] (XY-blurred occupancy) and
+ * clamp_bits (raw <= 1 mask).  voxels/probs are written only when non-NULL.
+ * ntaps == 0 means kernel=None (no blur). */
+DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
+                    const float *trans /*NULL ok*/, const float *focal /*NULL ok*/,
+                    const float *scale /*NULL ok*/,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz, int scatter_mode,
+                    float *tr_pc, float *grid_xy, uint32_t *clamp_bits,
+                    float *mask, float *depth,
+                    float *voxels /*NULL ok*/, float *probs /*NULL ok*/,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of the whole path.  g_grid is a [P,Vz,V,V] scratch buffer.
+ * Upstream grads: g_mask, g_depth [P,V,V]; g_probs, g_voxels, g_tr_pc optional.
+ * Outputs: g_points [P,N,3], g_quat [P,4]; g_trans [P,3], g_focal [P],
+ * g_scale [P] written when the matching input was given and the pointer is
+ * non-NULL. */
+DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
+                    const float *trans, const float *focal, const float *scale,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz,
+                    const float *grid_xy, const uint32_t *clamp_bits,
+                    const float *g_mask /*NULL ok*/, const float *g_depth /*NULL ok*/,
+                    const float *g_probs /*NULL ok*/, const float *g_voxels /*NULL ok*/,
+                    const float *g_tr_pc /*NULL ok*/,
+                    float *g_grid, float *g_points, float *g_quat, float *g_trans,
+                    float *g_focal, float *g_scale,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPC_B200_H */

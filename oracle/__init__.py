@@ -1,0 +1,28 @@
+"""CPU oracle for the differentiable point-cloud projection path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it, and there only as the checker or as
+the timed CPU baseline -- never as the thing shipped.  The product path
+(``pytorch_unsup_pc_b200``) never imports this package and fails loudly when
+its CUDA library is missing.
+
+Contents
+--------
+``closed_form``  torch-on-CPU restatement of the reference algorithm
+                 (reference dtype flow: fp32 quaternion normalise + first
+                 Hamilton product, fp64 afterwards), each function citing the
+                 reference file:line it follows.  Gradients come from torch
+                 autograd over the restatement, exactly as the reference gets
+                 its own gradients.
+``ref_loader``   imports the *real* reference from ``/root/reference`` (only
+                 present in the build container, never on the GPU box) so the
+                 restatement can be pinned against it and golden vectors can
+                 be generated (``tests/golden/make_golden.py``).
+``config``       the handful of config keys the path reads, with the
+                 reference's defaults.
+
+Parity status: the reference ships no golden vectors;
+the oracle is pinned by executing the reference itself in the build container
+(``tests/test_oracle_pinning.py`` live, ``tests/golden/*.npz`` committed).
+"""

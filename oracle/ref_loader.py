@@ -1,0 +1,126 @@
+"""Load and drive the REAL reference implementation (build container only).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  ``/root/reference`` does not
+exist on the GPU box; nothing that runs there may call into this module
+(``available()`` is the guard).  It is used to
+
+* pin ``oracle.closed_form`` against the reference executed live
+  (tests/test_oracle_pinning.py), and
+* generate the committed golden vectors (tests/golden/make_golden.py).
+
+The reference cannot be imported unmodified under numpy 2.x:
+util/quaternion.py:22-23 evaluates ``np.maximum_sctype(np.float)`` at import
+time.  A two-line shim restores those names; no reference file is copied or
+edited.  The reference's own config loader (util/config.py:46,131-155) needs
+easydict and an unsafe ``yaml.load``; we hand the functions a plain attribute
+dict with the same keys instead.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+from .config import AttrDict
+
+REFERENCE_ROOT = os.environ.get("DPC_REFERENCE_ROOT", "/root/reference")
+_DPC = os.path.join(REFERENCE_ROOT, "dpc")
+
+_mods = None
+
+
+def available():
+    return os.path.isfile(os.path.join(_DPC, "util", "point_cloud_to.py"))
+
+
+def load():
+    """Import the reference's hot-path modules; returns a namespace dict."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % _DPC)
+    # numpy>=1.24 removed these; util/quaternion.py:22-23 needs them at import
+    if not hasattr(np, "float"):
+        np.float = float
+    if not hasattr(np, "maximum_sctype"):
+        np.maximum_sctype = lambda t: np.float64
+    if _DPC not in sys.path:
+        sys.path.insert(0, _DPC)
+    import util.point_cloud_to as pc_to
+    import util.drc as drc
+    import util.gauss_kernel as gk
+    import util.quaternion as quat
+    _mods = dict(pc_to=pc_to, drc=drc, gauss_kernel=gk, quaternion=quat)
+    return _mods
+
+
+def reference_cfg(experiment="chair_unsupervised", **overrides):
+    """default_config.yaml overlaid with experiments/<experiment>/config.yaml."""
+    import yaml
+    with open(os.path.join(_DPC, "resources", "default_config.yaml")) as f:
+        cfg = AttrDict(yaml.safe_load(f))
+    if experiment:
+        p = os.path.join(REFERENCE_ROOT, "experiments", experiment, "config.yaml")
+        with open(p) as f:
+            cfg.update(yaml.safe_load(f))
+    cfg.update(overrides)
+    return cfg
+
+
+@contextlib.contextmanager
+def _quiet():
+    # pointcloud2voxels3d_fast prints "Voxel_time ..." (point_cloud_to.py:85)
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def ref_smoothing_kernel(cfg, sigma):
+    return load()["gauss_kernel"].smoothing_kernel(cfg, sigma)
+
+
+def ref_project(cfg, point_cloud, transform, predicted_translation=None,
+                kernel=None, scaling_factor=None, focal_length=None):
+    """The reference's projection composed in its CUDA-branch order.
+
+    ``pointcloud_project_fast`` (point_cloud_to.py:191-263) skips the blur
+    when ``torch.cuda.is_available()`` is False (:206-212), so on this
+    CPU-only container we call the reference's own sub-functions in the order
+    the CUDA branch runs them.  ``kernel=None`` follows the TF original
+    (point_cloud.py:237-243): no blur, [P,Z,Y,X,1] layout.
+    Returns the same dict keys as the reference (fp64 tensors).
+    """
+    m = load()
+    pc_to, drc = m["pc_to"], m["drc"]
+    with _quiet():
+        tr_pc = pc_to.pc_perspective_transform(cfg, point_cloud, transform,
+                                               predicted_translation, focal_length)
+        voxels, _ = pc_to.pointcloud2voxels3d_fast(cfg, tr_pc, None)
+    voxels = voxels.unsqueeze(1)
+    voxels_raw = voxels
+    voxels = torch.clamp(voxels, 0.0, 1.0)
+    if kernel is not None:
+        voxels = pc_to.smoothen_voxels3d(cfg, voxels, kernel)
+    voxels = voxels.squeeze(1).unsqueeze(-1)
+    if scaling_factor is not None:
+        sz = scaling_factor.shape[0]
+        voxels = voxels * scaling_factor.reshape(sz, 1, 1, 1, 1)
+        voxels = torch.clamp(voxels, 0.0, 1.0)
+    proj, drc_probs = drc.drc_projection(voxels, cfg)
+    drc_probs = torch.flip(drc_probs, [2])
+    proj_depth = drc.drc_depth_projection(drc_probs, cfg)
+    proj = torch.flip(proj, [1])
+    return {"proj": proj, "voxels": voxels, "tr_pc": tr_pc, "voxels_rgb": None,
+            "proj_rgb": None, "drc_probs": drc_probs, "proj_depth": proj_depth,
+            "voxels_raw": voxels_raw.squeeze(1)}
+
+
+def ref_project_literal(cfg, point_cloud, transform, predicted_translation=None,
+                        kernel=None, scaling_factor=None, focal_length=None):
+    """The reference's ``pointcloud_project_fast`` called as-is (no blur on CPU)."""
+    with _quiet():
+        return load()["pc_to"].pointcloud_project_fast(
+            cfg, point_cloud, transform, predicted_translation, None, kernel,
+            scaling_factor=scaling_factor, focal_length=focal_length)

@@ -1,0 +1,294 @@
+// Pose + trilinear scatter (forward) and gather + pose adjoint (backward).
+//
+// Reference: quaternion.py:110-132, point_cloud_to.py:118-178 (pose),
+// point_cloud_to.py:10-87 (8x index_put_ scatter) and their autograd.
+//
+// Forward: one thread per point.  The pose math, perspective divide, cell
+// index and the eight trilinear weights are computed in registers and go
+// straight to eight fire-and-forget fp32 reductions (RED.E.ADD.F32) on the
+// grid, which sits in L2 (64 projections x 1 MiB = 64 MiB < 126 MB L2):
+// there is no compaction, no index tensor and no host sync.  Out-of-frustum
+// points are predicated off; out-of-range corners (coordinate exactly +0.5)
+// carry weight 0 and are dropped instead of faulting.
+//
+// Backward: one thread per point re-derives the identical cell (same device
+// function, same roundings -- forward and backward can never disagree on the
+// cell), gathers the eight grid gradients (atomic-free), applies the pose
+// adjoint in fp64 and block-reduces the per-projection quaternion /
+// translation / focal partial sums into a fixed-order two-stage reduction, so
+// every gradient is deterministic.
+#include "common.cuh"
+#include "pose.cuh"
+
+namespace dpc {
+
+constexpr int kPoseThreads = 256;
+
+int pose_partial_blocks(int N) { return (N + kPoseThreads - 1) / kPoseThreads; }
+
+template <bool WRITE_TRPC, bool SCATTER>
+__global__ void __launch_bounds__(kPoseThreads)
+pose_scatter_kernel(PoseArgs a, float *__restrict__ tr_pc, float *__restrict__ grid) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  if (n >= a.N) return;
+  const Quat q = load_quat(a.quat + 4 * b);
+  const bool has_t = a.trans != nullptr;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  if (has_t) {
+    t0 = a.trans[3 * b];
+    t1 = a.trans[3 * b + 1];
+    t2 = a.trans[3 * b + 2];
+  }
+  const double f = a.focal ? (double)a.focal[b] : a.focal_const;
+  const size_t pi = ((size_t)b * a.N + n) * 3;
+  const float p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
+  const PosePoint pp = pose_point(q, p0, p1, p2, has_t, t0, t1, t2, f, a.cam_dist);
+  if (WRITE_TRPC) {
+    tr_pc[pi] = (float)pp.u0;
+    tr_pc[pi + 1] = (float)pp.u1;
+    tr_pc[pi + 2] = (float)pp.u2;
+  }
+  if (SCATTER) {
+    const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
+    if (!c.valid) return;
+    float *g = grid + (size_t)b * a.Vz * a.V * a.V;
+    const double wz[2] = {1.0 - c.rz, c.rz}, wy[2] = {1.0 - c.ry, c.ry},
+                 wx[2] = {1.0 - c.rx, c.rx};
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int z = c.iz + dz, y = c.iy + dy;
+        if (z >= a.Vz || y >= a.V) continue;
+        const double wzy = wz[dz] * wy[dy];
+        float *row = g + ((size_t)z * a.V + y) * a.V;
+        atomicAdd(row + c.ix, (float)(wzy * wx[0]));
+        if (c.ix + 1 < a.V) atomicAdd(row + c.ix + 1, (float)(wzy * wx[1]));
+      }
+  }
+}
+
+__global__ void __launch_bounds__(kPoseThreads)
+scatter_trpc_kernel(const float *__restrict__ tr_pc, int N, int Vz, int V,
+                    float *__restrict__ grid) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  if (n >= N) return;
+  const size_t pi = ((size_t)b * N + n) * 3;
+  const Cell c = make_cell((double)tr_pc[pi], (double)tr_pc[pi + 1], (double)tr_pc[pi + 2], Vz, V);
+  if (!c.valid) return;
+  float *g = grid + (size_t)b * Vz * V * V;
+  const double wz[2] = {1.0 - c.rz, c.rz}, wy[2] = {1.0 - c.ry, c.ry}, wx[2] = {1.0 - c.rx, c.rx};
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int z = c.iz + dz, y = c.iy + dy;
+      if (z >= Vz || y >= V) continue;
+      const double wzy = wz[dz] * wy[dy];
+      float *row = g + ((size_t)z * V + y) * V;
+      atomicAdd(row + c.ix, (float)(wzy * wx[0]));
+      if (c.ix + 1 < V) atomicAdd(row + c.ix + 1, (float)(wzy * wx[1]));
+    }
+}
+
+// dL/du from the grid gradient at the eight corners (adjoint of the trilinear
+// weights): dL/dr_a = sum_corners G[corner] * (+-1) * prod of
+// the other two axes' weights; dL/du_a = (V_a - 1) dL/dr_a.
+__device__ __forceinline__ void gather_cell(const Cell &c, const float *__restrict__ g, int Vz,
+                                            int V, double &gz, double &gy, double &gx) {
+  double G[2][2][2];
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int z = c.iz + dz, y = c.iy + dy;
+      const bool ok = (z < Vz) && (y < V);
+      const float *row = g + ((size_t)(ok ? z : 0) * V + (ok ? y : 0)) * V;
+      G[dz][dy][0] = ok ? (double)__ldg(row + c.ix) : 0.0;
+      G[dz][dy][1] = (ok && c.ix + 1 < V) ? (double)__ldg(row + c.ix + 1) : 0.0;
+    }
+  const double wz[2] = {1.0 - c.rz, c.rz}, wy[2] = {1.0 - c.ry, c.ry}, wx[2] = {1.0 - c.rx, c.rx};
+  gz = gy = gx = 0.0;
+#pragma unroll
+  for (int d1 = 0; d1 < 2; ++d1)
+#pragma unroll
+    for (int d2 = 0; d2 < 2; ++d2) {
+      gz += wy[d1] * wx[d2] * (G[1][d1][d2] - G[0][d1][d2]);
+      gy += wz[d1] * wx[d2] * (G[d1][1][d2] - G[d1][0][d2]);
+      gx += wz[d1] * wy[d2] * (G[d1][d2][1] - G[d1][d2][0]);
+    }
+  gz *= (double)(Vz - 1);
+  gy *= (double)(V - 1);
+  gx *= (double)(V - 1);
+}
+
+__global__ void __launch_bounds__(kPoseThreads)
+gather_trpc_bwd_kernel(const float *__restrict__ tr_pc, int N, int Vz, int V,
+                       const float *__restrict__ g_grid, float *__restrict__ g_trpc) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  if (n >= N) return;
+  const size_t pi = ((size_t)b * N + n) * 3;
+  const Cell c = make_cell((double)tr_pc[pi], (double)tr_pc[pi + 1], (double)tr_pc[pi + 2], Vz, V);
+  double gz = 0, gy = 0, gx = 0;
+  if (c.valid) gather_cell(c, g_grid + (size_t)b * Vz * V * V, Vz, V, gz, gy, gx);
+  g_trpc[pi] = (float)gz;
+  g_trpc[pi + 1] = (float)gy;
+  g_trpc[pi + 2] = (float)gx;
+}
+
+// partials[b][block][8] = {dq^_w, dq^_x, dq^_y, dq^_z, dt0, dt1, dt2, df}
+__global__ void __launch_bounds__(kPoseThreads)
+gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
+                       const float *__restrict__ g_trpc, float *__restrict__ g_points,
+                       double *__restrict__ partials) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  const Quat q = load_quat(a.quat + 4 * b);
+  const bool has_t = a.trans != nullptr;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  if (has_t) {
+    t0 = a.trans[3 * b];
+    t1 = a.trans[3 * b + 1];
+    t2 = a.trans[3 * b + 2];
+  }
+  const double f = a.focal ? (double)a.focal[b] : a.focal_const;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n < a.N) {
+    const size_t pi = ((size_t)b * a.N + n) * 3;
+    const double p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
+    const PosePoint pp = pose_point(q, (float)p0, (float)p1, (float)p2, has_t, t0, t1, t2, f,
+                                    a.cam_dist);
+    double gu0 = 0, gu1 = 0, gu2 = 0;
+    if (g_grid) {
+      const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
+      if (c.valid) gather_cell(c, g_grid + (size_t)b * a.Vz * a.V * a.V, a.Vz, a.V, gu0, gu1, gu2);
+    }
+    if (g_trpc) {
+      gu0 += (double)g_trpc[pi];
+      gu1 += (double)g_trpc[pi + 1];
+      gu2 += (double)g_trpc[pi + 2];
+    }
+    // perspective adjoint
+    const double izc = 1.0 / pp.zc;
+    const double s12 = (pp.r1 * gu1 + pp.r2 * gu2) * izc;  // (p'1 g1 + p'2 g2)/zc
+    const double g0 = gu0 - f * s12 * izc;
+    const double g1 = f * gu1 * izc;
+    const double g2 = f * gu2 * izc;
+    // rotation adjoint for F(q^) = (w^2-|v|^2) p + 2 (v.p) v + 2 w (v x p)
+    const double w = q.w, vx = q.x, vy = q.y, vz = q.z;
+    const double vg = vx * g0 + vy * g1 + vz * g2;
+    const double vp = vx * p0 + vy * p1 + vz * p2;
+    const double gp = g0 * p0 + g1 * p1 + g2 * p2;
+    const double ww = w * w - (vx * vx + vy * vy + vz * vz);
+    // v x g
+    const double c0 = vy * g2 - vz * g1, c1 = vz * g0 - vx * g2, c2 = vx * g1 - vy * g0;
+    g_points[pi] = (float)(ww * g0 + 2.0 * vg * vx - 2.0 * w * c0);
+    g_points[pi + 1] = (float)(ww * g1 + 2.0 * vg * vy - 2.0 * w * c1);
+    g_points[pi + 2] = (float)(ww * g2 + 2.0 * vg * vz - 2.0 * w * c2);
+    // p x g
+    const double x0 = p1 * g2 - p2 * g1, x1 = p2 * g0 - p0 * g2, x2 = p0 * g1 - p1 * g0;
+    acc[0] = 2.0 * w * gp + 2.0 * (vx * x0 + vy * x1 + vz * x2);  // g.(v x p) = v.(p x g)
+    acc[1] = -2.0 * gp * vx + 2.0 * (vg * p0 + vp * g0) + 2.0 * w * x0;
+    acc[2] = -2.0 * gp * vy + 2.0 * (vg * p1 + vp * g1) + 2.0 * w * x1;
+    acc[3] = -2.0 * gp * vz + 2.0 * (vg * p2 + vp * g2) + 2.0 * w * x2;
+    acc[4] = g0 - gu0;  // dL/dt0 = dL/dp'0 - g_u0
+    acc[5] = g1;
+    acc[6] = g2;
+    acc[7] = s12;       // dL/df
+  }
+  // fixed-order block reduction: warp shuffles, then warps in index order
+  __shared__ double red[kPoseThreads / 32][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double v = 0;
+#pragma unroll
+    for (int wdx = 0; wdx < kPoseThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
+  }
+}
+
+// One warp per projection: sums the per-block partials in index order and
+// applies the quaternion-normalisation Jacobian
+//   dL/dq = (dL/dq^ - q^ (q^ . dL/dq^)) / |q|         (quaternion.py:119-121)
+__global__ void finalize_kernel(PoseArgs a, const double *__restrict__ pose_partials,
+                                int pose_blocks, const float *__restrict__ scale_partials,
+                                int scale_blocks, float *__restrict__ g_quat,
+                                float *__restrict__ g_trans, float *__restrict__ g_focal,
+                                float *__restrict__ g_scale) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x;
+  double v = 0;
+  if (lane < 8 && pose_partials) {
+    for (int k = 0; k < pose_blocks; ++k) v += pose_partials[((size_t)b * pose_blocks + k) * 8 + lane];
+  } else if (lane == 8 && scale_partials) {
+    for (int k = 0; k < scale_blocks; ++k) v += (double)scale_partials[(size_t)b * scale_blocks + k];
+  }
+  const double dw = __shfl_sync(0xffffffffu, v, 0), dx = __shfl_sync(0xffffffffu, v, 1),
+               dy = __shfl_sync(0xffffffffu, v, 2), dz = __shfl_sync(0xffffffffu, v, 3);
+  if (pose_partials) {
+    if (lane == 0 && g_quat) {
+      const Quat q = load_quat(a.quat + 4 * b);
+      const double dot = q.w * dw + q.x * dx + q.y * dy + q.z * dz;
+      g_quat[4 * b] = (float)((dw - q.w * dot) * q.inv_norm);
+      g_quat[4 * b + 1] = (float)((dx - q.x * dot) * q.inv_norm);
+      g_quat[4 * b + 2] = (float)((dy - q.y * dot) * q.inv_norm);
+      g_quat[4 * b + 3] = (float)((dz - q.z * dot) * q.inv_norm);
+    }
+    if (lane >= 4 && lane < 7 && g_trans) g_trans[3 * b + lane - 4] = (float)v;
+    if (lane == 7 && g_focal) g_focal[b] = (float)v;
+  }
+  if (lane == 8 && g_scale && scale_partials) g_scale[b] = (float)v;
+}
+
+// ---- launchers ---------------------------------------------------------------
+int launch_pose_scatter(const PoseArgs &a, float *tr_pc, float *grid, cudaStream_t s) {
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  if (tr_pc && grid)
+    pose_scatter_kernel<true, true><<<g, t, 0, s>>>(a, tr_pc, grid);
+  else if (grid)
+    pose_scatter_kernel<false, true><<<g, t, 0, s>>>(a, tr_pc, grid);
+  else
+    pose_scatter_kernel<true, false><<<g, t, 0, s>>>(a, tr_pc, grid);
+  return check_launch("pose_scatter");
+}
+
+int launch_scatter_trpc(const float *tr_pc, int P, int N, int Vz, int V, float *grid,
+                        cudaStream_t s) {
+  dim3 g(pose_partial_blocks(N), P), t(kPoseThreads);
+  scatter_trpc_kernel<<<g, t, 0, s>>>(tr_pc, N, Vz, V, grid);
+  return check_launch("scatter_trpc");
+}
+
+int launch_gather_pose_bwd(const PoseArgs &a, const float *g_grid, const float *g_trpc,
+                           float *g_points, double *partials, cudaStream_t s) {
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials);
+  return check_launch("gather_pose_bwd");
+}
+
+int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, const float *g_grid,
+                           float *g_trpc, cudaStream_t s) {
+  dim3 g(pose_partial_blocks(N), P), t(kPoseThreads);
+  gather_trpc_bwd_kernel<<<g, t, 0, s>>>(tr_pc, N, Vz, V, g_grid, g_trpc);
+  return check_launch("gather_trpc_bwd");
+}
+
+int launch_finalize(const PoseArgs &a, const double *pose_partials, int pose_blocks,
+                    const float *scale_partials, int scale_blocks, float *g_quat, float *g_trans,
+                    float *g_focal, float *g_scale, cudaStream_t s) {
+  finalize_kernel<<<a.P, 32, 0, s>>>(a, pose_partials, pose_blocks, scale_partials, scale_blocks,
+                                     g_quat, g_trans, g_focal, g_scale);
+  return check_launch("finalize");
+}
+
+}  // namespace dpc

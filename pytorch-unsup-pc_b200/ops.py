@@ -1,0 +1,328 @@
+"""PyTorch custom autograd ops over the C ABI (include/dpc_b200.h).
+
+PyTorch supplies device memory, the current stream and the autograd tape;
+every computation is one of the hand-written sm_100a kernels in csrc/.  All
+ops require contiguous fp32 CUDA tensors and raise otherwise -- there is no
+CPU or eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_ws_cache = {}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32(t, name, shape=None):
+    """Validate/normalise one tensor argument (None passes through)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: dpc_b200 has no CPU fallback" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t.contiguous()
+
+
+def make_params(cfg, P, N, flip_y=True):
+    """dpc_params from the reference's cfg keys (default_config.yaml:72-83)."""
+    V = int(cfg.vox_size)
+    vz = int(getattr(cfg, "vox_size_z", -1))
+    Vz = V if vz == -1 else vz
+    return _lib.Params(P=int(P), N=int(N), Vz=Vz, V=V,
+                       camera_distance=float(cfg.camera_distance),
+                       focal_length=float(cfg.focal_length),
+                       max_depth=float(getattr(cfg, "max_depth", 10.0)),
+                       drc_clip=float(getattr(cfg, "drc_logsum_clip_val", 1e-5)),
+                       drc_logsum=1 if getattr(cfg, "drc_logsum", True) else 0,
+                       flip_y=1 if flip_y else 0)
+
+
+def host_taps(kernel):
+    """[k1, k2, k3] conv3d kernels (or None) -> three flat fp32 HOST tensors.
+
+    The taps are kernel *arguments* (they ride in the constant bank), so they
+    must be readable by the host: CPU tensors -- what the reference's
+    ``smoothing_kernel`` returns -- are used as they are; CUDA tensors cost a
+    device-to-host copy and a sync."""
+    if kernel is None:
+        return None
+    if len(kernel) != 3:
+        raise ValueError("kernel must be the [X, Y, Z] list smoothing_kernel returns")
+    out = []
+    for k in kernel:
+        k = torch.as_tensor(k).detach().reshape(-1).to(device="cpu", dtype=torch.float32)
+        if k.numel() % 2 == 0 or k.numel() > _lib.MAX_TAPS:
+            raise ValueError("Gaussian kernel size %d must be odd and <= %d"
+                             % (k.numel(), _lib.MAX_TAPS))
+        out.append(k.contiguous())
+    return tuple(out)
+
+
+def _tap_args(taps):
+    if taps is None:
+        return (None, 0, None, 0, None, 0)
+    args = []
+    for k in taps:
+        args += [ctypes.c_void_p(k.data_ptr()), int(k.numel())]
+    return tuple(args)
+
+
+def _workspace(params, device):
+    """One cached workspace per (device, size class); stream-ordered reuse."""
+    need = _lib.load().dpc_workspace_bytes(ctypes.byref(params))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+class ProjectFn(torch.autograd.Function):
+    """pointcloud_project_fast (point_cloud_to.py:191-263) as ONE op.
+
+    forward : memset + pose/scatter + blur XY (in place) + blur Z/DRC  (4 launches)
+    backward: DRC reverse scan/blur Z adjoint + blur XY adjoint + gather/pose
+              adjoint + finalize                                       (4 launches)
+    Saved for backward: the inputs, the XY-blurred grid and a 1-bit clamp mask.
+    """
+
+    @staticmethod
+    def forward(ctx, points, quat, trans, focal, scale, params, taps, want_voxels, want_probs,
+                mode):
+        lib = _lib.load()
+        dev = points.device
+        P, N, Vz, V = params.P, params.N, params.Vz, params.V
+        f32 = dict(dtype=torch.float32, device=dev)
+        tr_pc = torch.empty(P, N, 3, **f32)
+        grid_xy = torch.empty(P, Vz, V, V, **f32)
+        bits = torch.empty(P, Vz, V, V // 32, dtype=torch.int32, device=dev)
+        mask = torch.empty(P, V, V, **f32)
+        depth = torch.empty(P, V, V, **f32)
+        voxels = torch.empty(P, Vz, V, V, **f32) if want_voxels else None
+        probs = torch.empty(Vz + 1, P, V, V, **f32) if want_probs else None
+        ws = _workspace(params, dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_project_fwd(
+                ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
+                _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), _ptr(grid_xy), _ptr(bits),
+                _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws), ws.numel(),
+                _stream(dev))
+        _lib.check(st, "project_fwd")
+        ctx.save_for_backward(points, quat, trans, focal, scale, grid_xy, bits)
+        ctx.params, ctx.taps = params, taps
+        ctx.set_materialize_grads(False)
+        return mask, depth, tr_pc, voxels, probs
+
+    @staticmethod
+    def backward(ctx, g_mask, g_depth, g_trpc, g_voxels, g_probs):
+        lib = _lib.load()
+        points, quat, trans, focal, scale, grid_xy, bits = ctx.saved_tensors
+        params = ctx.params
+        dev = points.device
+        P, N, Vz, V = params.P, params.N, params.Vz, params.V
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_mask = _f32(g_mask, "g_mask", (P, V, V))
+        g_depth = _f32(g_depth, "g_depth", (P, V, V))
+        g_trpc = _f32(g_trpc, "g_tr_pc", (P, N, 3))
+        g_voxels = _f32(g_voxels, "g_voxels", (P, Vz, V, V))
+        g_probs = _f32(g_probs, "g_probs", (Vz + 1, P, V, V))
+        g_grid = torch.empty(P, Vz, V, V, **f32)
+        g_points = torch.empty(P, N, 3, **f32)
+        g_quat = torch.empty(P, 4, **f32)
+        g_trans = torch.empty(P, 3, **f32) if trans is not None else None
+        g_focal = torch.empty(P, **f32) if focal is not None else None
+        g_scale = torch.empty(P, **f32) if scale is not None else None
+        ws = _workspace(params, dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_project_bwd(
+                ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
+                _ptr(scale), *_tap_args(ctx.taps), _ptr(grid_xy), _ptr(bits), _ptr(g_mask),
+                _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid),
+                _ptr(g_points), _ptr(g_quat), _ptr(g_trans), _ptr(g_focal), _ptr(g_scale),
+                _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "project_bwd")
+        return (g_points, g_quat, g_trans, g_focal, g_scale, None, None, None, None, None)
+
+
+class PoseFn(torch.autograd.Function):
+    """pc_perspective_transform (point_cloud_to.py:118-178, quaternion branch)."""
+
+    @staticmethod
+    def forward(ctx, points, quat, trans, focal, params):
+        lib = _lib.load()
+        dev = points.device
+        tr_pc = torch.empty(params.P, params.N, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_pose_fwd(ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans),
+                                  _ptr(focal), _ptr(tr_pc), _stream(dev))
+        _lib.check(st, "pose_fwd")
+        ctx.save_for_backward(points, quat, trans, focal)
+        ctx.params = params
+        return tr_pc
+
+    @staticmethod
+    def backward(ctx, g_trpc):
+        lib = _lib.load()
+        points, quat, trans, focal = ctx.saved_tensors
+        params = ctx.params
+        dev = points.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_trpc = _f32(g_trpc, "g_tr_pc", (params.P, params.N, 3))
+        g_points = torch.empty(params.P, params.N, 3, **f32)
+        g_quat = torch.empty(params.P, 4, **f32)
+        g_trans = torch.empty(params.P, 3, **f32) if trans is not None else None
+        g_focal = torch.empty(params.P, **f32) if focal is not None else None
+        ws = _workspace(params, dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_pose_bwd(ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans),
+                                  _ptr(focal), _ptr(g_trpc), _ptr(g_points), _ptr(g_quat),
+                                  _ptr(g_trans), _ptr(g_focal), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "pose_bwd")
+        return g_points, g_quat, g_trans, g_focal, None
+
+
+class ScatterFn(torch.autograd.Function):
+    """pointcloud2voxels3d_fast (point_cloud_to.py:10-87): tr_pc -> raw grid."""
+
+    @staticmethod
+    def forward(ctx, tr_pc, params, mode):
+        lib = _lib.load()
+        dev = tr_pc.device
+        grid = torch.empty(params.P, params.Vz, params.V, params.V, dtype=torch.float32, device=dev)
+        ws = _workspace(params, dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_scatter_fwd(ctypes.byref(params), _ptr(tr_pc), _ptr(grid), int(mode),
+                                     _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "scatter_fwd")
+        ctx.save_for_backward(tr_pc)
+        ctx.params = params
+        return grid
+
+    @staticmethod
+    def backward(ctx, g_grid):
+        lib = _lib.load()
+        (tr_pc,) = ctx.saved_tensors
+        params = ctx.params
+        dev = tr_pc.device
+        g_grid = _f32(g_grid, "g_grid", (params.P, params.Vz, params.V, params.V))
+        g_trpc = torch.empty_like(tr_pc)
+        with torch.cuda.device(dev):
+            st = lib.dpc_scatter_bwd(ctypes.byref(params), _ptr(tr_pc), _ptr(g_grid), _ptr(g_trpc),
+                                     _stream(dev))
+        _lib.check(st, "scatter_bwd")
+        return g_trpc, None, None
+
+
+def _blur3d(x, params, taps):
+    lib = _lib.load()
+    dev = x.device
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        st = lib.dpc_blur3d(ctypes.byref(params), _ptr(x), _ptr(out), *_tap_args(taps),
+                            _stream(dev))
+    _lib.check(st, "blur3d")
+    return out
+
+
+class BlurFn(torch.autograd.Function):
+    """smoothen_voxels3d (point_cloud_to.py:90-103).  Symmetric taps with zero
+    'same' padding are self-adjoint, so backward is the same three passes."""
+
+    @staticmethod
+    def forward(ctx, vox, params, taps):
+        ctx.params, ctx.taps = params, taps
+        return _blur3d(vox, params, taps)
+
+    @staticmethod
+    def backward(ctx, g):
+        params = ctx.params
+        g = _f32(g, "g_voxels", (params.P, params.Vz, params.V, params.V))
+        # adjoint of a cross-correlation = correlation with the reversed taps
+        taps = tuple(torch.flip(k, [0]).contiguous() for k in ctx.taps)
+        return _blur3d(g, params, taps), None, None
+
+
+class DrcFn(torch.autograd.Function):
+    """drc_projection (drc.py:114-129) + depth (drc.py:152-160): voxels ->
+    (mask, probs, depth); no blur, no scaling, flips as asked in params."""
+
+    @staticmethod
+    def forward(ctx, vox, params):
+        lib = _lib.load()
+        dev = vox.device
+        P, Vz, V = params.P, params.Vz, params.V
+        f32 = dict(dtype=torch.float32, device=dev)
+        mask = torch.empty(P, V, V, **f32)
+        depth = torch.empty(P, V, V, **f32)
+        probs = torch.empty(Vz + 1, P, V, V, **f32)
+        with torch.cuda.device(dev):
+            st = lib.dpc_drc_fwd(ctypes.byref(params), _ptr(vox), _ptr(mask), _ptr(depth),
+                                 _ptr(probs), _stream(dev))
+        _lib.check(st, "drc_fwd")
+        ctx.save_for_backward(vox)
+        ctx.params = params
+        ctx.set_materialize_grads(False)
+        return mask, probs, depth
+
+    @staticmethod
+    def backward(ctx, g_mask, g_probs, g_depth):
+        lib = _lib.load()
+        (vox,) = ctx.saved_tensors
+        params = ctx.params
+        dev = vox.device
+        P, Vz, V = params.P, params.Vz, params.V
+        g_mask = _f32(g_mask, "g_mask", (P, V, V))
+        g_depth = _f32(g_depth, "g_depth", (P, V, V))
+        g_probs = _f32(g_probs, "g_probs", (Vz + 1, P, V, V))
+        g_vox = torch.empty_like(vox)
+        ws = _workspace(params, dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_drc_bwd(ctypes.byref(params), _ptr(vox), _ptr(g_mask), _ptr(g_depth),
+                                 _ptr(g_probs), _ptr(g_vox), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "drc_bwd")
+        return g_vox, None
+
+
+class DepthFromProbsFn(torch.autograd.Function):
+    """drc_depth_projection on stored probabilities (drc.py:152-160)."""
+
+    @staticmethod
+    def forward(ctx, probs, params):
+        lib = _lib.load()
+        dev = probs.device
+        depth = torch.empty(params.P, params.V, params.V, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_depth_from_probs_fwd(ctypes.byref(params), _ptr(probs), _ptr(depth),
+                                              _stream(dev))
+        _lib.check(st, "depth_from_probs_fwd")
+        ctx.params = params
+        return depth
+
+    @staticmethod
+    def backward(ctx, g_depth):
+        lib = _lib.load()
+        params = ctx.params
+        dev = g_depth.device
+        g_depth = _f32(g_depth, "g_depth", (params.P, params.V, params.V))
+        g_probs = torch.empty(params.Vz + 1, params.P, params.V, params.V, dtype=torch.float32,
+                              device=dev)
+        with torch.cuda.device(dev):
+            st = lib.dpc_depth_from_probs_bwd(ctypes.byref(params), _ptr(g_depth), _ptr(g_probs),
+                                              _stream(dev))
+        _lib.check(st, "depth_from_probs_bwd")
+        return g_probs, None

@@ -1,0 +1,147 @@
+"""Drop-in mirror of the reference's util/point_cloud_to.py (hot-path functions).
+
+Same names, argument order and output layouts as the reference; outputs are
+fp32 (the reference's are fp64 because of a float64 constant in
+quaternion_conjugate; its callers only subtract and sum them).
+"""
+import contextlib
+
+import torch
+
+from . import _lib, ops
+
+_options = {"voxels": True, "drc_probs": True, "deterministic": False}
+
+
+def set_outputs(voxels=None, drc_probs=None):
+    """Choose whether ``pointcloud_project_fast`` materialises the two large,
+    rarely-consumed outputs (``voxels`` [P,Vz,V,V,1], ``drc_probs``
+    [Vz+1,P,V,V,1]).  Default: both on, exactly like the reference.  The
+    reference model only consumes proj / proj_depth / drc_probs
+    (model_pc_to.py:266-269) and drc_probs only when ``drc_weight > 0``."""
+    if voxels is not None:
+        _options["voxels"] = bool(voxels)
+    if drc_probs is not None:
+        _options["drc_probs"] = bool(drc_probs)
+
+
+def set_deterministic(flag=True):
+    """Use the sort-then-segment scatter: bit-exact run to run (the default
+    scatter uses fp32 reductions whose order varies)."""
+    _options["deterministic"] = bool(flag)
+
+
+@contextlib.contextmanager
+def options(**kw):
+    old = dict(_options)
+    try:
+        for k, v in kw.items():
+            if k not in _options:
+                raise KeyError(k)
+            _options[k] = bool(v)
+        yield
+    finally:
+        _options.update(old)
+
+
+def _scatter_mode():
+    return _lib.SCATTER_SORTED if _options["deterministic"] else _lib.SCATTER_ATOMIC
+
+
+def _check_quaternion_cfg(cfg):
+    if not getattr(cfg, "pose_quaternion", True):
+        raise NotImplementedError(
+            "pose_quaternion: false (4x4 camera matrices) is not supported; the reference's "
+            "matrix branch itself fails (point_cloud_to.py:153, UnboundLocalError)")
+
+
+def _vec(t, name, P):
+    """[P,1] / [P] -> contiguous [P] (scaling_factor, focal_length)."""
+    if t is None:
+        return None
+    t = ops._f32(t, name)
+    if t.numel() != P:
+        raise ValueError("%s: expected %d values, got shape %s" % (name, P, tuple(t.shape)))
+    return t.reshape(P)
+
+
+def pc_perspective_transform(cfg, point_cloud, transform, predicted_translation=None,
+                             focal_length=None):
+    """point_cloud [P,N,3], transform [P,4] quaternion -> [P,N,3] in (z,y,x)
+    order (point_cloud_to.py:118-178)."""
+    _check_quaternion_cfg(cfg)
+    pts = ops._f32(point_cloud, "point_cloud")
+    if pts.dim() != 3 or pts.shape[-1] != 3:
+        raise ValueError("point_cloud must be [P,N,3], got %s" % (tuple(pts.shape),))
+    P, N, _ = pts.shape
+    quat = ops._f32(transform, "transform", (P, 4))
+    trans = ops._f32(predicted_translation, "predicted_translation", (P, 3))
+    focal = _vec(focal_length, "focal_length", P)
+    params = ops.make_params(cfg, P, N)
+    return ops.PoseFn.apply(pts, quat, trans, focal, params)
+
+
+def pointcloud2voxels3d_fast(cfg, pc, rgb):
+    """pc [P,N,3] (already transformed) -> (voxels [P,Vz,V,V], None)
+    (point_cloud_to.py:10-87).  Points outside [-0.5,0.5]^3 are dropped."""
+    if rgb is not None:
+        raise NotImplementedError("the rgb branch is broken in the reference "
+                                  "(point_cloud_to.py:64) and not part of this path")
+    pts = ops._f32(pc, "pc")
+    if pts.dim() != 3 or pts.shape[-1] != 3:
+        raise ValueError("pc must be [P,N,3], got %s" % (tuple(pts.shape),))
+    params = ops.make_params(cfg, pts.shape[0], pts.shape[1])
+    return ops.ScatterFn.apply(pts, params, _scatter_mode()), None
+
+
+def smoothen_voxels3d(cfg, voxels, kernel):
+    """voxels [P,1,Vz,V,V], kernel = [k1,k2,k3] -> same shape
+    (point_cloud_to.py:90-103)."""
+    vox = ops._f32(voxels, "voxels")
+    if vox.dim() != 5 or vox.shape[1] != 1:
+        raise ValueError("voxels must be [P,1,Vz,V,V], got %s" % (tuple(vox.shape),))
+    P, _, Vz, V, V2 = vox.shape
+    params = ops.make_params(cfg, P, 0)
+    if (params.Vz, params.V, params.V) != (Vz, V, V2):
+        raise ValueError("voxels shape %s does not match cfg grid %s"
+                         % (tuple(vox.shape), (params.Vz, params.V, params.V)))
+    out = ops.BlurFn.apply(vox.reshape(P, Vz, V, V), params, ops.host_taps(kernel))
+    return out.reshape(P, 1, Vz, V, V)
+
+
+def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation, all_rgb,
+                            kernel=None, scaling_factor=None, focal_length=None):
+    """The whole projection (point_cloud_to.py:191-263): returns the reference's
+    dict {proj [P,V,V,1], voxels [P,Vz,V,V,1], tr_pc [P,N,3], voxels_rgb,
+    proj_rgb, drc_probs [Vz+1,P,V,V,1], proj_depth [P,V,V,1]}.
+
+    The blur always runs when ``kernel`` is given (the reference's CUDA branch,
+    :207-209); ``kernel=None`` means no blur with the TF original's layout."""
+    _check_quaternion_cfg(cfg)
+    if all_rgb is not None:
+        raise NotImplementedError("all_rgb: the rgb branch is broken in the reference "
+                                  "(point_cloud_to.py:64) and not part of this path")
+    if getattr(cfg, "ptn_max_projection", False):
+        raise NotImplementedError("ptn_max_projection is broken in the reference "
+                                  "(point_cloud_to.py:234,242) and not supported")
+    pts = ops._f32(point_cloud, "point_cloud")
+    if pts.dim() != 3 or pts.shape[-1] != 3:
+        raise ValueError("point_cloud must be [P,N,3], got %s" % (tuple(pts.shape),))
+    P, N, _ = pts.shape
+    quat = ops._f32(transform, "transform", (P, 4))
+    trans = ops._f32(predicted_translation, "predicted_translation", (P, 3))
+    scale = _vec(scaling_factor, "scaling_factor", P)
+    focal = _vec(focal_length, "focal_length", P)
+    params = ops.make_params(cfg, P, N, flip_y=True)
+    mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
+        pts, quat, trans, focal, scale, params, ops.host_taps(kernel),
+        _options["voxels"], _options["drc_probs"], _scatter_mode())
+    return {
+        "proj": mask.unsqueeze(-1),
+        "voxels": None if voxels is None else voxels.unsqueeze(-1),
+        "tr_pc": tr_pc,
+        "voxels_rgb": None,
+        "proj_rgb": None,
+        "drc_probs": None if probs is None else probs.unsqueeze(-1),
+        "proj_depth": depth.unsqueeze(-1),
+    }

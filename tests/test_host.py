@@ -1,0 +1,85 @@
+"""CPU: host logic and the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle.config import default_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import pytorch_unsup_pc_b200 as dpc
+    header = open(os.path.join(ROOT, "include", "dpc_b200.h")).read()
+    declared = set(re.findall(r"DPC_API[^;(]*?\b(dpc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(dpc.library_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    # the ctypes prototypes cover exactly the declared surface
+    assert declared == set(dpc._lib.SIGNATURES)
+    assert dpc.version() == 100
+
+
+def test_workspace_bytes_and_params_struct():
+    import pytorch_unsup_pc_b200 as dpc
+    from pytorch_unsup_pc_b200 import ops
+    cfg = default_cfg(vox_size=64, vox_size_z=32)
+    p = ops.make_params(cfg, 64, 8000)
+    assert (p.P, p.N, p.Vz, p.V) == (64, 8000, 32, 64)
+    assert p.camera_distance == 2.0 and p.focal_length == 1.875 and p.max_depth == 10.0
+    assert p.drc_logsum == 1 and p.flip_y == 1
+    need = dpc._lib.load().dpc_workspace_bytes(ctypes.byref(p))
+    # pose partials (P*ceil(N/256)*8 doubles) + scale partials + 2*P*N sort keys
+    assert need >= 64 * 32 * 8 * 8 + 2 * 64 * 8000 * 4
+    assert need % 256 == 0
+
+
+def test_cpu_tensors_are_refused():
+    import pytorch_unsup_pc_b200 as dpc
+    cfg = default_cfg(vox_size=32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dpc.pointcloud_project_fast(cfg, torch.zeros(1, 4, 3), torch.ones(1, 4), None, None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dpc.pc_perspective_transform(cfg, torch.zeros(1, 4, 3), torch.ones(1, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dpc.drc_projection(torch.zeros(1, 32, 32, 32, 1), cfg)
+
+
+def test_unsupported_reference_branches_raise():
+    import pytorch_unsup_pc_b200 as dpc
+    cfg = default_cfg(vox_size=32)
+    with pytest.raises(NotImplementedError):
+        dpc.pointcloud_project_fast(cfg, torch.zeros(1, 4, 3), torch.ones(1, 4), None,
+                                    torch.zeros(1, 4, 3))
+    with pytest.raises(NotImplementedError):
+        dpc.pointcloud_project_fast(default_cfg(pose_quaternion=False), torch.zeros(1, 4, 3),
+                                    torch.ones(1, 4, 4), None, None)
+    with pytest.raises(NotImplementedError):
+        dpc.pointcloud_project_fast(default_cfg(ptn_max_projection=True), torch.zeros(1, 4, 3),
+                                    torch.ones(1, 4), None, None)
+
+
+def test_host_taps_validation():
+    from pytorch_unsup_pc_b200 import ops
+    import pytorch_unsup_pc_b200 as dpc
+    cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
+    taps = ops.host_taps(dpc.smoothing_kernel(cfg, 3.0))
+    assert [t.numel() for t in taps] == [21, 21, 21]
+    assert all(t.dtype == torch.float32 and not t.is_cuda for t in taps)
+    assert abs(taps[0].sum().item() - 1) < 1e-6
+    with pytest.raises(ValueError):
+        ops.host_taps([torch.ones(4)] * 3)
+    with pytest.raises(ValueError):
+        ops.host_taps([torch.ones(23)] * 3)
+    assert ops.host_taps(None) is None
+
+
+def test_anisotropic_kernel_lengths():
+    import pytorch_unsup_pc_b200 as dpc
+    cfg = default_cfg(vox_size=64, vox_size_z=32, pc_gauss_kernel_size=21)
+    k = dpc.smoothing_kernel(cfg, 3.0)
+    assert [tuple(t.shape) for t in k] == [(1, 1, 1, 1, 21), (1, 1, 1, 21, 1), (1, 1, 11, 1, 1)]
