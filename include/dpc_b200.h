@@ -149,6 +149,25 @@ DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const floa
                     float *g_focal, float *g_scale,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- measurement aid (bench.py): runs dpc_project_fwd + dpc_project_bwd
+ * `iters` times with a CUDA event recorded on `stream` after every stage and
+ * returns the average duration of each stage in milliseconds.  Synchronises
+ * the stream once per iteration -- for profiling only.  Stage order:
+ * 0 memset(grid) | 1 pose+scatter | 2 blur XY fwd | 3 blur Z + DRC fwd |
+ * 4 DRC bwd + blur Z adjoint | 5 blur XY adjoint | 6 gather + pose adjoint |
+ * 7 finalize (quaternion/translation/focal/scale reductions). */
+#define DPC_PROFILE_STAGES 8
+DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,
+                    const float *trans, const float *focal, const float *scale,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz, int scatter_mode,
+                    float *tr_pc, float *grid_xy, uint32_t *clamp_bits, float *mask, float *depth,
+                    const float *g_mask, const float *g_depth,
+                    float *g_grid, float *g_points, float *g_quat, float *g_trans,
+                    float *g_focal, float *g_scale,
+                    void *workspace, size_t workspace_bytes, void *stream,
+                    int iters, float *stage_ms_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,13 @@ SIGNATURES = {
                        + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
                        + [c_void_p] * 2 + [c_void_p] * 5 + [c_void_p] * 6
                        + [c_void_p, c_size_t, c_void_p],
+    "dpc_project_profile": [_P] + [c_void_p] * 5
+                           + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
+                           + [c_void_p] * 5 + [c_void_p] * 2 + [c_void_p] * 6
+                           + [c_void_p, c_size_t, c_void_p, c_int, c_void_p],
 }
+PROFILE_STAGES = ("memset", "pose_scatter", "blur_xy_fwd", "blurz_drc_fwd", "drc_blurz_bwd",
+                  "blur_xy_bwd", "gather_pose_bwd", "finalize")
 _RESTYPES = {"dpc_last_error": ctypes.c_char_p, "dpc_workspace_bytes": c_size_t}
 
 _lib = None

@@ -28,6 +28,14 @@ int check_launch(const char *what) {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Profiling hook (dpc_project_profile): when set, an event is recorded after
+// every stage of dpc_project_fwd / dpc_project_bwd on the launching stream.
+static thread_local cudaEvent_t *tl_stage_events = nullptr;
+static thread_local int tl_stage_idx = 0;
+static inline void stage_mark(cudaStream_t s) {
+  if (tl_stage_events) cudaEventRecord(tl_stage_events[tl_stage_idx++], s);
+}
+
 struct Workspace {
   double *pose_partials;
   float *scale_partials;
@@ -249,13 +257,16 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
   DPC_TRY(check_taps(tz, kz, "taps_z"));
   cudaStream_t s = (cudaStream_t)stream;
   const PoseArgs pa = pose_args(p, points, quat, trans, focal);
+  stage_mark(s);
   if (scatter_mode == DPC_SCATTER_SORTED) {
     DPC_TRY(check_ws(p, workspace, workspace_bytes));
     const Workspace w = carve(p, workspace);
+    stage_mark(s);
     DPC_TRY(launch_scatter_sorted(&pa, nullptr, p->P, p->N, p->Vz, p->V, tr_pc, grid_xy, w.sorted,
                                   w.sorted_bytes, s));
   } else if (scatter_mode == DPC_SCATTER_ATOMIC) {
     if (cudaMemsetAsync(grid_xy, 0, grid_bytes(p), s) != cudaSuccess) return check_launch("memset");
+    stage_mark(s);
     DPC_TRY(launch_pose_scatter(pa, tr_pc, grid_xy, s));
   } else {
     set_error("unknown scatter mode %d", scatter_mode);
@@ -265,8 +276,12 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
   BlurXYArgs b;
   b.src = grid_xy; b.dst = grid_xy; b.bits_out = clamp_bits; b.bits_in = nullptr;
   b.planes = p->P * p->Vz; b.V = p->V; b.clamp_in = true;
+  stage_mark(s);
   DPC_TRY(launch_blur_xy(b, tx, kx, ty, ky, s));
-  return launch_blurz_drc_fwd(drc_args(p, grid_xy, scale), tz, kz, mask, depth, voxels, probs, s);
+  stage_mark(s);
+  DPC_TRY(launch_blurz_drc_fwd(drc_args(p, grid_xy, scale), tz, kz, mask, depth, voxels, probs, s));
+  stage_mark(s);
+  return DPC_OK;
 }
 
 int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
@@ -285,8 +300,10 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
   const PoseArgs pa = pose_args(p, points, quat, trans, focal);
+  stage_mark(s);
   DPC_TRY(launch_drc_blurz_bwd(drc_args(p, grid_xy, scale), tz, kz, g_mask, g_depth, g_probs,
                                g_voxels, g_grid, w.scale_partials, s));
+  stage_mark(s);
   BlurXYArgs b;
   b.src = g_grid; b.dst = g_grid; b.bits_out = nullptr; b.bits_in = clamp_bits;
   b.planes = p->P * p->Vz; b.V = p->V; b.clamp_in = false;
@@ -295,11 +312,53 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   for (int i = 0; i < kx; ++i) rx[i] = tx[kx - 1 - i];
   for (int i = 0; i < ky; ++i) ry[i] = ty[ky - 1 - i];
   DPC_TRY(launch_blur_xy(b, rx, kx, ry, ky, s));
+  stage_mark(s);
   DPC_TRY(launch_gather_pose_bwd(pa, g_grid, g_tr_pc, g_points, w.pose_partials, s));
-  return launch_finalize(pa, w.pose_partials, pose_partial_blocks(p->N),
-                         scale ? w.scale_partials : nullptr, drc_scale_partial_blocks(p->V), g_quat,
-                         trans ? g_trans : nullptr, focal ? g_focal : nullptr,
-                         scale ? g_scale : nullptr, s);
+  stage_mark(s);
+  DPC_TRY(launch_finalize(pa, w.pose_partials, pose_partial_blocks(p->N),
+                          scale ? w.scale_partials : nullptr, drc_scale_partial_blocks(p->V),
+                          g_quat, trans ? g_trans : nullptr, focal ? g_focal : nullptr,
+                          scale ? g_scale : nullptr, s));
+  stage_mark(s);
+  return DPC_OK;
+}
+
+int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,
+                        const float *trans, const float *focal, const float *scale,
+                        const float *tx, int kx, const float *ty, int ky, const float *tz, int kz,
+                        int scatter_mode, float *tr_pc, float *grid_xy, uint32_t *clamp_bits,
+                        float *mask, float *depth, const float *g_mask, const float *g_depth,
+                        float *g_grid, float *g_points, float *g_quat, float *g_trans,
+                        float *g_focal, float *g_scale, void *workspace, size_t workspace_bytes,
+                        void *stream, int iters, float *stage_ms_host) {
+  if (iters < 1 || !stage_ms_host) { set_error("profile: iters >= 1 and stage_ms_host required"); return DPC_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t ev[DPC_PROFILE_STAGES + 2];
+  for (auto &e : ev) cudaEventCreate(&e);
+  double acc[DPC_PROFILE_STAGES] = {0};
+  int rc = DPC_OK;
+  for (int it = 0; it < iters && rc == DPC_OK; ++it) {
+    tl_stage_events = ev;
+    tl_stage_idx = 0;
+    rc = dpc_project_fwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, scatter_mode,
+                         tr_pc, grid_xy, clamp_bits, mask, depth, nullptr, nullptr, workspace,
+                         workspace_bytes, stream);
+    const int nf = tl_stage_idx;  // 5 events: start + 4 stages
+    if (rc == DPC_OK)
+      rc = dpc_project_bwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, grid_xy,
+                           clamp_bits, g_mask, g_depth, nullptr, nullptr, nullptr, g_grid, g_points,
+                           g_quat, g_trans, g_focal, g_scale, workspace, workspace_bytes, stream);
+    const int nb = tl_stage_idx;  // + 5 events
+    tl_stage_events = nullptr;
+    if (rc != DPC_OK) break;
+    if (cudaStreamSynchronize(s) != cudaSuccess) { rc = check_launch("profile sync"); break; }
+    int k = 0;
+    for (int i = 1; i < nf; ++i, ++k) { float ms; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); acc[k] += ms; }
+    for (int i = nf + 1; i < nb; ++i, ++k) { float ms; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); acc[k] += ms; }
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  for (int k = 0; k < DPC_PROFILE_STAGES; ++k) stage_ms_host[k] = (float)(acc[k] / iters);
+  return rc;
 }
 
 }  // extern "C"

@@ -134,10 +134,13 @@ def test_frustum_edges(dpc):
                                       CF.smoothing_taps(cfg, 1.0))
     for k in ("proj", "proj_depth", "tr_pc", "voxels", "drc_probs"):
         assert _golden.rel_err(out[k], orc[k]) < FWD_TOL, k
-    raw, _ = dpc.pointcloud2voxels3d_fast(cfg, orc["tr_pc"].float().to(dev), None)
-    assert _golden.rel_err(raw, orc["voxels_raw"]) < FWD_TOL
+    # stand-alone scatter of the fp32 tr_pc (rounding to fp32 can move a point
+    # onto the face, so the oracle scatters the same fp32 values)
+    tr32 = orc["tr_pc"].float()
+    raw, _ = dpc.pointcloud2voxels3d_fast(cfg, tr32.to(dev), None)
+    assert _golden.rel_err(raw, CF.scatter_trilinear(cfg, tr32.double(), drop_oob=True)) < FWD_TOL
     # mass conservation: every in-frustum point deposits total weight 1
-    inside = ((orc["tr_pc"] >= -0.5) & (orc["tr_pc"] <= 0.5)).all(-1).sum().item()
+    inside = ((tr32 >= -0.5) & (tr32 <= 0.5)).all(-1).sum().item()
     assert abs(raw.sum().item() - inside) < 1e-4
 
 
@@ -148,9 +151,6 @@ def test_all_points_outside_and_single_point(dpc):
     kern = CF.smoothing_taps(cfg, 1.0)
     far = torch.full((1, 5, 3), 3.0, device=dev, requires_grad=True)
     out = dpc.pointcloud_project_fast(cfg, far, quat, None, None, kern)
-    # empty grid: every voxel clipped to c => mask = 1 - exp(c) (1-c)^Z
-    c, Z = cfg.drc_logsum_clip_val, 32
-    want = torch.tensor(c).exp().item() * (1 - (1 - c) ** Z) if False else None
     orc = CF.project(cfg, far.detach().cpu(), quat.cpu(), None, kern, None)
     assert _golden.rel_err(out["proj"], orc["proj"]) < FWD_TOL
     assert _golden.rel_err(out["proj_depth"], orc["proj_depth"]) < FWD_TOL
