@@ -118,16 +118,17 @@ DPC_API int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, 
 
 /* ---- a12+a13: point_cloud_to.py:191-263 pointcloud_project_fast ----------
  * The whole path in one call: pose -> scatter -> clamp -> blur XY (in place)
- * -> blur Z + scale + clip + DRC ray march (+ Y flips).
- * Saved for backward: grid_xy [P,Vz,V,V] (XY-blurred occupancy) and
- * clamp_bits (raw <= 1 mask).  voxels/probs are written only when non-NULL.
+ * -> blur Z (in place) + scale + clip + DRC ray march (+ Y flips).
+ * Saved for backward: grid_b [P,Vz,V,V] (the blurred occupancy B, before
+ * scaling) and clamp_bits (raw <= 1 mask).  voxels/probs are written only
+ * when non-NULL.
  * ntaps == 0 means kernel=None (no blur). */
 DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
                     const float *trans /*NULL ok*/, const float *focal /*NULL ok*/,
                     const float *scale /*NULL ok*/,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,
                     const float *taps_z_host, int kz, int scatter_mode,
-                    float *tr_pc, float *grid_xy, uint32_t *clamp_bits,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits,
                     float *mask, float *depth,
                     float *voxels /*NULL ok*/, float *probs /*NULL ok*/,
                     void *workspace, size_t workspace_bytes, void *stream);
@@ -141,7 +142,7 @@ DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const floa
                     const float *trans, const float *focal, const float *scale,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,
                     const float *taps_z_host, int kz,
-                    const float *grid_xy, const uint32_t *clamp_bits,
+                    const float *grid_b, const uint32_t *clamp_bits,
                     const float *g_mask /*NULL ok*/, const float *g_depth /*NULL ok*/,
                     const float *g_probs /*NULL ok*/, const float *g_voxels /*NULL ok*/,
                     const float *g_tr_pc /*NULL ok*/,
@@ -161,7 +162,7 @@ DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const 
                     const float *trans, const float *focal, const float *scale,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,
                     const float *taps_z_host, int kz, int scatter_mode,
-                    float *tr_pc, float *grid_xy, uint32_t *clamp_bits, float *mask, float *depth,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, float *mask, float *depth,
                     const float *g_mask, const float *g_depth,
                     float *g_grid, float *g_points, float *g_quat, float *g_trans,
                     float *g_focal, float *g_scale,

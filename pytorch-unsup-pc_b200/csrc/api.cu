@@ -214,8 +214,8 @@ int dpc_drc_fwd(const dpc_params *p, const float *voxels, float *mask, float *de
                 void *stream) {
   DPC_TRY(check_params(p, false));
   DPC_REQUIRE(voxels); DPC_REQUIRE(mask);
-  return launch_blurz_drc_fwd(drc_args(p, voxels, nullptr), nullptr, 0, mask, depth, nullptr, probs,
-                              (cudaStream_t)stream);
+  return launch_blurz_drc_fwd(drc_args(p, voxels, nullptr), nullptr, 0, nullptr, mask, depth,
+                              nullptr, probs, (cudaStream_t)stream);
 }
 
 int dpc_drc_bwd(const dpc_params *p, const float *voxels, const float *g_mask, const float *g_depth,
@@ -247,11 +247,11 @@ int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, float *g
 int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
                     const float *ty, int ky, const float *tz, int kz, int scatter_mode,
-                    float *tr_pc, float *grid_xy, uint32_t *clamp_bits, float *mask, float *depth,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, float *mask, float *depth,
                     float *voxels, float *probs, void *workspace, size_t workspace_bytes,
                     void *stream) {
   DPC_TRY(check_params(p, true));
-  DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_xy); DPC_REQUIRE(clamp_bits);
+  DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
   DPC_REQUIRE(mask);
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
   DPC_TRY(check_taps(tz, kz, "taps_z"));
@@ -262,37 +262,39 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
     DPC_TRY(check_ws(p, workspace, workspace_bytes));
     const Workspace w = carve(p, workspace);
     stage_mark(s);
-    DPC_TRY(launch_scatter_sorted(&pa, nullptr, p->P, p->N, p->Vz, p->V, tr_pc, grid_xy, w.sorted,
+    DPC_TRY(launch_scatter_sorted(&pa, nullptr, p->P, p->N, p->Vz, p->V, tr_pc, grid_b, w.sorted,
                                   w.sorted_bytes, s));
   } else if (scatter_mode == DPC_SCATTER_ATOMIC) {
-    if (cudaMemsetAsync(grid_xy, 0, grid_bytes(p), s) != cudaSuccess) return check_launch("memset");
+    if (cudaMemsetAsync(grid_b, 0, grid_bytes(p), s) != cudaSuccess) return check_launch("memset");
     stage_mark(s);
-    DPC_TRY(launch_pose_scatter(pa, tr_pc, grid_xy, s));
+    DPC_TRY(launch_pose_scatter(pa, tr_pc, grid_b, s));
   } else {
     set_error("unknown scatter mode %d", scatter_mode);
     return DPC_ERR_ARG;
   }
   // clamp(raw,0,1) + raw<=1 mask + blur X + blur Y, in place (identity taps when kernel=None)
   BlurXYArgs b;
-  b.src = grid_xy; b.dst = grid_xy; b.bits_out = clamp_bits; b.bits_in = nullptr;
+  b.src = grid_b; b.dst = grid_b; b.bits_out = clamp_bits; b.bits_in = nullptr;
   b.planes = p->P * p->Vz; b.V = p->V; b.clamp_in = true;
   stage_mark(s);
   DPC_TRY(launch_blur_xy(b, tx, kx, ty, ky, s));
   stage_mark(s);
-  DPC_TRY(launch_blurz_drc_fwd(drc_args(p, grid_xy, scale), tz, kz, mask, depth, voxels, probs, s));
+  // blur Z + scale + clip + DRC; the blurred occupancy overwrites grid in place (saved for bwd)
+  DPC_TRY(launch_blurz_drc_fwd(drc_args(p, grid_b, scale), tz, kz, grid_b, mask, depth, voxels,
+                               probs, s));
   stage_mark(s);
   return DPC_OK;
 }
 
 int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
-                    const float *ty, int ky, const float *tz, int kz, const float *grid_xy,
+                    const float *ty, int ky, const float *tz, int kz, const float *grid_b,
                     const uint32_t *clamp_bits, const float *g_mask, const float *g_depth,
                     const float *g_probs, const float *g_voxels, const float *g_tr_pc,
                     float *g_grid, float *g_points, float *g_quat, float *g_trans, float *g_focal,
                     float *g_scale, void *workspace, size_t workspace_bytes, void *stream) {
   DPC_TRY(check_params(p, true));
-  DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_xy); DPC_REQUIRE(clamp_bits);
+  DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
   DPC_REQUIRE(g_grid); DPC_REQUIRE(g_points);
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
   DPC_TRY(check_taps(tz, kz, "taps_z"));
@@ -301,7 +303,7 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   cudaStream_t s = (cudaStream_t)stream;
   const PoseArgs pa = pose_args(p, points, quat, trans, focal);
   stage_mark(s);
-  DPC_TRY(launch_drc_blurz_bwd(drc_args(p, grid_xy, scale), tz, kz, g_mask, g_depth, g_probs,
+  DPC_TRY(launch_drc_blurz_bwd(drc_args(p, grid_b, scale), tz, kz, g_mask, g_depth, g_probs,
                                g_voxels, g_grid, w.scale_partials, s));
   stage_mark(s);
   BlurXYArgs b;
@@ -326,7 +328,7 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
 int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,
                         const float *trans, const float *focal, const float *scale,
                         const float *tx, int kx, const float *ty, int ky, const float *tz, int kz,
-                        int scatter_mode, float *tr_pc, float *grid_xy, uint32_t *clamp_bits,
+                        int scatter_mode, float *tr_pc, float *grid_b, uint32_t *clamp_bits,
                         float *mask, float *depth, const float *g_mask, const float *g_depth,
                         float *g_grid, float *g_points, float *g_quat, float *g_trans,
                         float *g_focal, float *g_scale, void *workspace, size_t workspace_bytes,
@@ -341,11 +343,11 @@ int dpc_project_profile(const dpc_params *p, const float *points, const float *q
     tl_stage_events = ev;
     tl_stage_idx = 0;
     rc = dpc_project_fwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, scatter_mode,
-                         tr_pc, grid_xy, clamp_bits, mask, depth, nullptr, nullptr, workspace,
+                         tr_pc, grid_b, clamp_bits, mask, depth, nullptr, nullptr, workspace,
                          workspace_bytes, stream);
     const int nf = tl_stage_idx;  // 5 events: start + 4 stages
     if (rc == DPC_OK)
-      rc = dpc_project_bwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, grid_xy,
+      rc = dpc_project_bwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, grid_b,
                            clamp_bits, g_mask, g_depth, nullptr, nullptr, nullptr, g_grid, g_points,
                            g_quat, g_trans, g_focal, g_scale, workspace, workspace_bytes, stream);
     const int nb = tl_stage_idx;  // + 5 events

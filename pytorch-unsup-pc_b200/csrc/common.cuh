@@ -94,9 +94,11 @@ struct DrcArgs {
   float cam_dist, max_depth, clip;
   int logsum, flip_y;
 };
-int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *mask, float *depth,
-                         float *voxels, float *probs, cudaStream_t s);
+// bsave (NULL ok, may alias a.grid): receives blurZ(grid), the tensor the backward needs
+int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave, float *mask,
+                         float *depth, float *voxels, float *probs, cudaStream_t s);
 int drc_scale_partial_blocks(int V);
+// a.grid = blurZ-ed grid saved by the forward (or the plain voxels when kz == 0)
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
                          float *g_grid, float *scale_partials, cudaStream_t s);

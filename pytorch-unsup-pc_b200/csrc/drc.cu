@@ -9,25 +9,33 @@
 // One thread owns one ray (b, y, x); a warp owns 32 consecutive x, so every
 // global access is a full 128-byte line.  The Z blur is a register ring of
 // 2R+1 values indexed at compile time (the z loop is unrolled by the ring
-// length), so the blurred occupancy never exists in memory: each value is
-// consumed by the ray march as soon as it is produced.
+// length) with the taps in uniform registers; each blurred value is consumed
+// by the ray march as soon as it is produced and written back IN PLACE over
+// the column it came from (an input is always loaded R steps before its slot
+// is overwritten), so the buffer the backward needs costs no extra memory.
 //
-//   vox_k = clamp(s * blurZ(grid)_k, 0, 1)        v_k = clamp(vox_k, c, 1-c)
+//   vox_k = clamp(s * B_k, 0, 1)   B = blurZ(grid_xy)     v_k = clamp(vox_k, c, 1-c)
 //   p_k = e_k v_k T_k,  T_{k+1} = T_k (1 - v_k),  p_Z = e_Z T_Z,  e_0 = e_Z = exp(c)
 //   mask = sum_{k<Z} p_k      depth = sum_k psi_k p_k
 //
 // The reference evaluates the same product as exp(cumsum(log(.))) in fp64; the
-// product form needs no transcendentals and agrees to fp32 rounding.
+// product form needs no transcendentals and agrees to fp32 rounding.  Optional
+// behaviour (no scale, product-form DRC) is folded into the clamp bounds
+// (+-inf) instead of branches.
 //
 // Backward (rewritten without cancellation): with a_k the
 // upstream weight of p_k and D_j = dL/dT_j,
 //   D_Z = a_Z e_Z,   D_k = a_k e_k v_k + (1 - v_k) D_{k+1},
 //   dL/dv_k = T_k (a_k e_k - D_{k+1}).
-// Sweep 1 (forward in z) recomputes blurZ and T_k into shared memory
-// ([k][thread] layout, conflict-free); sweep 2 (reverse in z) runs the D
-// recursion, applies the clip/clamp gates and the scale, and streams the
-// result through the same register ring to apply the Z-blur adjoint on the
-// way out.  dL/dscale is reduced per block in fixed order.
+// Sweep 1 (forward in z) copies the saved B column to shared memory
+// ([k][thread], conflict-free) and checkpoints T at every ring-length block;
+// sweep 2 walks the blocks in reverse: it re-expands T inside the block from
+// the checkpoint, runs the D recursion downwards, applies the clip/clamp
+// gates and the scale, and pushes the result through the register ring to
+// apply the Z-blur adjoint on the way out.  dL/dscale is reduced per block
+// in fixed order.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace dpc {
@@ -38,8 +46,10 @@ int drc_scale_partial_blocks(int V) { return V * V / kRayThreads; }
 
 struct RayConst {
   int P, Vz, V, VV;
-  float inv_z, depth0, max_depth, clip, one_minus_clip, exp_clip;
-  int logsum, flip_y, has_scale;
+  float inv_z, depth0, max_depth, exp_clip;
+  float lo_s, hi_s;   // clamp(s*B, 0, 1) bounds; +-inf when there is no scaling factor
+  float lo_c, hi_c;   // DRC clip bounds;        +-inf for the product form
+  int flip_y, has_scale;
 };
 
 static RayConst make_ray_const(const DrcArgs &a) {
@@ -48,59 +58,69 @@ static RayConst make_ray_const(const DrcArgs &a) {
   c.inv_z = 1.0f / (float)a.Vz;
   c.depth0 = a.cam_dist - 0.5f;
   c.max_depth = a.max_depth;
-  c.clip = a.clip;
-  c.one_minus_clip = 1.0f - a.clip;
   c.exp_clip = a.logsum ? (float)exp((double)a.clip) : 1.0f;
-  c.logsum = a.logsum;
-  c.flip_y = a.flip_y;
   c.has_scale = a.scale != nullptr;
+  c.lo_s = c.has_scale ? 0.f : -INFINITY;
+  c.hi_s = c.has_scale ? 1.f : INFINITY;
+  c.lo_c = a.logsum ? a.clip : -INFINITY;
+  c.hi_c = a.logsum ? 1.0f - a.clip : INFINITY;
+  c.flip_y = a.flip_y;
   return c;
 }
 
 template <int R>
 __device__ __forceinline__ float ring_dot(const float (&ring)[2 * R + 1], const Taps<R> &taps,
-                                          int first /*compile-time*/) {
+                                          int first /*compile-time*/, bool reversed) {
   constexpr int W = 2 * R + 1;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int t = 0; t < W; ++t) {
     const float v = ring[(first + t) % W];
-    if (t % 3 == 0) s0 = fmaf(taps.k[t], v, s0);
-    else if (t % 3 == 1) s1 = fmaf(taps.k[t], v, s1);
-    else s2 = fmaf(taps.k[t], v, s2);
+    const float k = reversed ? taps.k[W - 1 - t] : taps.k[t];
+    if (t % 3 == 0) s0 = fmaf(k, v, s0);
+    else if (t % 3 == 1) s1 = fmaf(k, v, s1);
+    else s2 = fmaf(k, v, s2);
   }
   return (s0 + s1) + s2;
 }
 
-// Streams blurZ(col)_z for z = 0..Vz-1 to `sink(z, value)`.
+// Streams blurZ(col)_z for z = 0..Vz-1 to `sink(j, z, value)`; j is the
+// compile-time position inside the current block of W steps.
 template <int R, typename Sink>
-__device__ __forceinline__ void stream_blur_z(const float *__restrict__ col, int Vz, int VV,
+__device__ __forceinline__ void stream_blur_z(const float *col, int Vz, int VV,
                                               const Taps<R> &taps, Sink &&sink) {
   constexpr int W = 2 * R + 1;
   if (R == 0) {
 #pragma unroll 8
-    for (int z = 0; z < Vz; ++z) sink(z, taps.k[0] * __ldg(col + (size_t)z * VV));
+    for (int z = 0; z < Vz; ++z) {
+      sink(1, z, taps.k[0] * *col);
+      col += VV;
+    }
     return;
   }
   float ring[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) ring[i] = 0.f;
+  const float *ld = col;
 #pragma unroll
-  for (int i = 0; i < R; ++i) ring[i] = (i < Vz) ? __ldg(col + (size_t)i * VV) : 0.f;
+  for (int i = 0; i < R; ++i) {
+    ring[i] = (i < Vz) ? *ld : 0.f;
+    ld += VV;
+  }
 #pragma unroll 1
   for (int z0 = 0; z0 < Vz; z0 += W) {
     float nxt[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      const int zin = z0 + j + R;
-      nxt[j] = (zin < Vz) ? __ldg(col + (size_t)zin * VV) : 0.f;
+      nxt[j] = (z0 + j + R < Vz) ? *ld : 0.f;
+      ld += VV;
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       const int z = z0 + j;
       if (z < Vz) {
         ring[(j + R) % W] = nxt[j];
-        sink(z, ring_dot<R>(ring, taps, (j + R + 1) % W));
+        sink(j, z, ring_dot<R>(ring, taps, (j + R + 1) % W, false));
       }
     }
   }
@@ -115,125 +135,165 @@ __device__ __forceinline__ void ray_index(const RayConst &c, int &b, int &yx, in
   out_idx = b * c.VV + yo * c.V + x;
 }
 
-template <int R>
+// EXTRA: the optional voxels / probs outputs exist.  `grid` and `bsave` may
+// alias (in-place save), so neither is __restrict__.
+template <int R, bool EXTRA>
 __global__ void __launch_bounds__(kRayThreads)
-blurz_drc_fwd_kernel(const float *__restrict__ grid, const float *__restrict__ scale, RayConst c,
-                     const Taps<R> kz, float *__restrict__ mask, float *__restrict__ depth,
-                     float *__restrict__ voxels, float *__restrict__ probs) {
+blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayConst c,
+                     const Taps<R> kz, float *bsave, float *__restrict__ mask,
+                     float *__restrict__ depth, float *__restrict__ voxels,
+                     float *__restrict__ probs) {
   int b, yx, oi;
   ray_index(c, b, yx, oi);
-  const float *col = grid + (size_t)b * c.Vz * c.VV + yx;
+  const size_t col0 = (size_t)b * c.Vz * c.VV + yx;
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
-  float T = 1.f, m = 0.f, d = 0.f;
+  float T = 1.f, m = 0.f, d = 0.f, kf = 0.f;
+  float *bs = bsave ? bsave + col0 : nullptr;
+  float *vx = (EXTRA && voxels) ? voxels + col0 : nullptr;
+  float *pr = (EXTRA && probs) ? probs + oi : nullptr;
   const size_t pstride = (size_t)c.P * c.VV;
-  stream_blur_z<R>(col, c.Vz, c.VV, kz, [&](int z, float bz) {
-    float vox = bz;
-    if (c.has_scale) vox = fminf(fmaxf(s * bz, 0.f), 1.f);
-    if (voxels) voxels[(size_t)b * c.Vz * c.VV + (size_t)z * c.VV + yx] = vox;
-    const float v = c.logsum ? fminf(fmaxf(vox, c.clip), c.one_minus_clip) : vox;
+  stream_blur_z<R>(grid + col0, c.Vz, c.VV, kz, [&](int j, int z, float bz) {
+    if (bs) { *bs = bz; bs += c.VV; }
+    const float vox = fminf(fmaxf(s * bz, c.lo_s), c.hi_s);
+    const float v = fminf(fmaxf(vox, c.lo_c), c.hi_c);
     float p = v * T;
-    if (z == 0) p *= c.exp_clip;
-    if (probs) probs[(size_t)z * pstride + oi] = p;
+    if ((R == 0 || j == 0) && z == 0) p *= c.exp_clip;   // only block position 0 can be z == 0
+    if (EXTRA) {
+      if (vx) { *vx = vox; vx += c.VV; }
+      if (pr) { *pr = p; pr += pstride; }
+    }
     m += p;
-    d = fmaf((float)z * c.inv_z + c.depth0, p, d);
+    d = fmaf(fmaf(kf, c.inv_z, c.depth0), p, d);
+    kf += 1.f;
     T *= (1.f - v);
   });
   const float pz = c.exp_clip * T;
-  if (probs) probs[(size_t)c.Vz * pstride + oi] = pz;
+  if (EXTRA && pr) *pr = pz;
   mask[oi] = m;
   if (depth) depth[oi] = fmaf(c.max_depth, pz, d);
 }
 
-template <int R>
+template <int R, bool EXTRA>
 __global__ void __launch_bounds__(kRayThreads)
-drc_blurz_bwd_kernel(const float *__restrict__ grid, const float *__restrict__ scale, RayConst c,
+drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ scale, RayConst c,
                      const Taps<R> kz, const float *__restrict__ g_mask,
                      const float *__restrict__ g_depth, const float *__restrict__ g_probs,
                      const float *__restrict__ g_voxels, float *__restrict__ g_grid,
                      float *__restrict__ scale_partials) {
   constexpr int W = 2 * R + 1;
+  constexpr int BL = (R == 0) ? 16 : W;   // block length, a multiple of the ring length
   extern __shared__ float sm[];
-  float *sB = sm + threadIdx.x;                        // [Vz][threads]  blurZ value
-  float *sT = sm + c.Vz * kRayThreads + threadIdx.x;   // [Vz][threads]  transmittance T_k
+  float *sB = sm + threadIdx.x;                        // [Vz][threads]     saved blurZ value
+  float *sC = sm + c.Vz * kRayThreads + threadIdx.x;   // [nblk][threads]   T at block starts
   int b, yx, oi;
   ray_index(c, b, yx, oi);
-  const float *col = grid + (size_t)b * c.Vz * c.VV + yx;
+  const size_t col0 = (size_t)b * c.Vz * c.VV + yx;
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
-  // ---- sweep 1: recompute blurZ and T_k ----
-  float T = 1.f;
-  stream_blur_z<R>(col, c.Vz, c.VV, kz, [&](int z, float bz) {
-    sB[z * kRayThreads] = bz;
-    sT[z * kRayThreads] = T;
-    float vox = bz;
-    if (c.has_scale) vox = fminf(fmaxf(s * bz, 0.f), 1.f);
-    const float v = c.logsum ? fminf(fmaxf(vox, c.clip), c.one_minus_clip) : vox;
-    T *= (1.f - v);
-  });
+  const int nblk = (c.Vz + BL - 1) / BL;
+
+  auto occupancy = [&](float bz, float &sb, float &vox) -> float {
+    sb = s * bz;
+    vox = fminf(fmaxf(sb, c.lo_s), c.hi_s);
+    return fminf(fmaxf(vox, c.lo_c), c.hi_c);
+  };
+
+  // ---- sweep 1: stage the column, checkpoint the transmittance ----
+  {
+    const float *ld = bgrid + col0;
+    float T = 1.f;
+#pragma unroll 1
+    for (int bi = 0; bi < nblk; ++bi) {
+      sC[bi * kRayThreads] = T;
+      float vals[BL];
+#pragma unroll
+      for (int j = 0; j < BL; ++j) {
+        vals[j] = (bi * BL + j < c.Vz) ? __ldg(ld) : 0.f;
+        ld += c.VV;
+      }
+#pragma unroll
+      for (int j = 0; j < BL; ++j) {
+        const int z = bi * BL + j;
+        if (z < c.Vz) {
+          sB[z * kRayThreads] = vals[j];
+          float sb, vox;
+          T *= (1.f - occupancy(vals[j], sb, vox));
+        }
+      }
+    }
+  }
   // ---- sweep 2: reverse scan + Z-blur adjoint ----
   const float gm = g_mask ? __ldg(g_mask + oi) : 0.f;
   const float gd = g_depth ? __ldg(g_depth + oi) : 0.f;
   const size_t pstride = (size_t)c.P * c.VV;
   float D = c.max_depth * gd;
-  if (g_probs) D += __ldg(g_probs + (size_t)c.Vz * pstride + oi);
+  if (EXTRA && g_probs) D += __ldg(g_probs + (size_t)c.Vz * pstride + oi);
   D *= c.exp_clip;
   float ds = 0.f;
-  float *gcol = g_grid + (size_t)b * c.Vz * c.VV + yx;
-  const float *gvcol = g_voxels ? g_voxels + (size_t)b * c.Vz * c.VV + yx : nullptr;
-
-  auto step = [&](int k) -> float {  // returns dL/d(grid_xy blurred in z)_k
-    const float bz = sB[k * kRayThreads];
-    const float Tk = sT[k * kRayThreads];
-    const float sb = s * bz;
-    float vox = bz;
-    if (c.has_scale) vox = fminf(fmaxf(sb, 0.f), 1.f);
-    const float v = c.logsum ? fminf(fmaxf(vox, c.clip), c.one_minus_clip) : vox;
-    float a = fmaf((float)k * c.inv_z + c.depth0, gd, gm);
-    if (g_probs) a += __ldg(g_probs + (size_t)k * pstride + oi);
-    if (k == 0) a *= c.exp_clip;
-    float gv = Tk * (a - D);
-    D = fmaf(a, v, (1.f - v) * D);
-    if (c.logsum) gv = (vox >= c.clip && vox <= c.one_minus_clip) ? gv : 0.f;
-    if (gvcol) gv += __ldg(gvcol + (size_t)k * c.VV);
-    if (c.has_scale) {
-      gv = (sb >= 0.f && sb <= 1.f) ? gv : 0.f;
-      ds = fmaf(gv, bz, ds);
-      gv *= s;
-    }
-    return gv;
-  };
-
-  if (R == 0) {
-#pragma unroll 4
-    for (int k = c.Vz - 1; k >= 0; --k) gcol[(size_t)k * c.VV] = kz.k[0] * step(k);
-  } else {
-    float ring[W];
+  float ring[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) ring[i] = 0.f;
-    const int total = c.Vz + R;  // steps m = 0 .. Vz+R-1, input k = Vz-1-m, output z = k+R
+  for (int i = 0; i < W; ++i) ring[i] = 0.f;
+
 #pragma unroll 1
-    for (int m0 = 0; m0 < total; m0 += W) {
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int z0 = bi * BL;
+    // re-expand T_k inside the block from its checkpoint
+    float tseg[BL];
+    {
+      float T = sC[bi * kRayThreads];
 #pragma unroll
-      for (int j = 0; j < W; ++j) {
-        const int m = m0 + j;
-        if (m < total) {
-          const int k = c.Vz - 1 - m;
-          ring[j] = (k >= 0) ? step(k) : 0.f;
-          const int z = k + R;
-          if (z < c.Vz) {
-            // out[z] = sum_t kz[t] * in[z + t - R]; in[i] sits in slot (Vz-1-i) % W = (m - t) % W
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int t = 0; t < W; ++t) {
-              // adjoint of a correlation = correlation with the reversed taps
-              const float v = ring[(j - t + W) % W];
-              if (t % 3 == 0) s0 = fmaf(kz.k[W - 1 - t], v, s0);
-              else if (t % 3 == 1) s1 = fmaf(kz.k[W - 1 - t], v, s1);
-              else s2 = fmaf(kz.k[W - 1 - t], v, s2);
-            }
-            gcol[(size_t)z * c.VV] = (s0 + s1) + s2;
-          }
+      for (int j = 0; j < BL; ++j) {
+        tseg[j] = T;
+        if (z0 + j < c.Vz) {
+          float sb, vox;
+          T *= (1.f - occupancy(sB[(z0 + j) * kRayThreads], sb, vox));
         }
       }
+    }
+    // pointers at k = z0 + BL - 1 (outputs at z = k + R); they walk downwards
+    float *gout = g_grid + col0 + (ptrdiff_t)(z0 + BL - 1 + R) * c.VV;
+    const float *gpr =
+        (EXTRA && g_probs) ? g_probs + (ptrdiff_t)(z0 + BL - 1) * (ptrdiff_t)pstride + oi : nullptr;
+    const float *gvx =
+        (EXTRA && g_voxels) ? g_voxels + col0 + (ptrdiff_t)(z0 + BL - 1) * c.VV : nullptr;
+    float kf = (float)(z0 + BL - 1);
+#pragma unroll
+    for (int j = BL - 1; j >= 0; --j) {
+      const int k = z0 + j;
+      float gB = 0.f;
+      if (k < c.Vz) {
+        const float bz = sB[k * kRayThreads];
+        float sb, vox;
+        const float v = occupancy(bz, sb, vox);
+        float a = fmaf(fmaf(kf, c.inv_z, c.depth0), gd, gm);
+        if (EXTRA && gpr) a += __ldg(gpr);
+        if (j == 0 && k == 0) a *= c.exp_clip;
+        float gv = tseg[j] * (a - D);
+        D = fmaf(a, v, (1.f - v) * D);
+        gv = (vox >= c.lo_c && vox <= c.hi_c) ? gv : 0.f;
+        if (EXTRA && gvx) gv += __ldg(gvx);
+        gv = (sb >= c.lo_s && sb <= c.hi_s) ? gv : 0.f;
+        ds = fmaf(gv, bz, ds);
+        gB = gv * s;
+      }
+      ring[j % W] = gB;
+      // out[z] = sum_t kz[2R-t] * in[k + t], z = k + R   (adjoint = reversed taps)
+      if (k + R < c.Vz) *gout = ring_dot<R>(ring, kz, j % W, true);
+      gout -= c.VV;
+      if (EXTRA) {
+        if (gpr) gpr -= pstride;
+        if (gvx) gvx -= c.VV;
+      }
+      kf -= 1.f;
+    }
+  }
+  if (R > 0) {
+    // flush: inputs k = -1 .. -R are zero; they complete the outputs z = R-1 .. 0
+    float *gout = g_grid + col0 + (ptrdiff_t)(R - 1) * c.VV;
+#pragma unroll
+    for (int j = BL - 1; j >= BL - R; --j) {
+      ring[j % W] = 0.f;
+      if (j - BL + R < c.Vz) *gout = ring_dot<R>(ring, kz, j % W, true);
+      gout -= c.VV;
     }
   }
   // ---- dL/dscale: fixed-order block reduction ----
@@ -254,13 +314,15 @@ drc_blurz_bwd_kernel(const float *__restrict__ grid, const float *__restrict__ s
 
 template <int R>
 __global__ void __launch_bounds__(kRayThreads)
-blur_z_kernel(const float *__restrict__ src, float *__restrict__ dst, int Vz, int VV,
-              const Taps<R> kz) {
+blur_z_kernel(const float *src, float *dst, int Vz, int VV, const Taps<R> kz) {
   const int ray = blockIdx.x * kRayThreads + threadIdx.x;
   const int b = ray / VV, yx = ray - b * VV;
   const float *col = src + (size_t)b * Vz * VV + yx;
   float *out = dst + (size_t)b * Vz * VV + yx;
-  stream_blur_z<R>(col, Vz, VV, kz, [&](int z, float bz) { out[(size_t)z * VV] = bz; });
+  stream_blur_z<R>(col, Vz, VV, kz, [&](int, int, float bz) {
+    *out = bz;
+    out += VV;
+  });
 }
 
 __global__ void __launch_bounds__(kRayThreads)
@@ -296,8 +358,8 @@ static Taps<R> z_taps(const float *tz, int kz, int r) {
   return make_taps<R>(tz + off, 2 * r + 1);
 }
 
-static int check_ray_geometry(const DrcArgs &a) {
-  if ((a.V * a.V) % kRayThreads != 0) {
+static int check_ray_geometry(int V) {
+  if ((V * V) % kRayThreads != 0) {
     set_error("drc: V*V must be a multiple of %d", kRayThreads);
     return DPC_ERR_ARG;
   }
@@ -313,44 +375,63 @@ static int check_ray_geometry(const DrcArgs &a) {
     else { set_error("z tap radius %d > 10 unsupported", r); return DPC_ERR_ARG; } \
   } while (0)
 
-int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *mask, float *depth,
-                         float *voxels, float *probs, cudaStream_t s) {
-  if (int e = check_ray_geometry(a)) return e;
+int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave, float *mask,
+                         float *depth, float *voxels, float *probs, cudaStream_t s) {
+  if (int e = check_ray_geometry(a.V)) return e;
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
   const int blocks = a.P * a.V * a.V / kRayThreads;
-  DPC_DISPATCH_R(r, blurz_drc_fwd_kernel<R><<<blocks, kRayThreads, 0, s>>>(
-                        a.grid, a.scale, c, z_taps<R>(tz, kz, r), mask, depth, voxels, probs));
+  if (voxels || probs) {
+    DPC_DISPATCH_R(r, blurz_drc_fwd_kernel<R, true><<<blocks, kRayThreads, 0, s>>>(
+                          a.grid, a.scale, c, z_taps<R>(tz, kz, r), bsave, mask, depth, voxels,
+                          probs));
+  } else {
+    DPC_DISPATCH_R(r, blurz_drc_fwd_kernel<R, false><<<blocks, kRayThreads, 0, s>>>(
+                          a.grid, a.scale, c, z_taps<R>(tz, kz, r), bsave, mask, depth, nullptr,
+                          nullptr));
+  }
   return check_launch("blurz_drc_fwd");
+}
+
+template <int R, bool EXTRA>
+static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
+                           const float *g_mask, const float *g_depth, const float *g_probs,
+                           const float *g_voxels, float *g_grid, float *scale_partials,
+                           cudaStream_t s) {
+  constexpr int BL = (R == 0) ? 16 : 2 * R + 1;
+  const int nblk = (a.Vz + BL - 1) / BL;
+  const size_t smem = (size_t)(a.Vz + nblk) * kRayThreads * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(drc_blurz_bwd_kernel<R, EXTRA>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  const int blocks = a.P * a.V * a.V / kRayThreads;
+  drc_blurz_bwd_kernel<R, EXTRA><<<blocks, kRayThreads, smem, s>>>(
+      a.grid, a.scale, c, taps, g_mask, g_depth, g_probs, g_voxels, g_grid,
+      a.scale ? scale_partials : nullptr);
 }
 
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
                          float *g_grid, float *scale_partials, cudaStream_t s) {
-  if (int e = check_ray_geometry(a)) return e;
+  if (int e = check_ray_geometry(a.V)) return e;
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
-  const int blocks = a.P * a.V * a.V / kRayThreads;
-  const size_t smem = (size_t)2 * a.Vz * kRayThreads * sizeof(float);
-  if (smem > 200 * 1024) {
-    set_error("drc_bwd: vox_size_z %d too large", a.Vz);
-    return DPC_ERR_ARG;
+  if (g_probs || g_voxels) {
+    DPC_DISPATCH_R(r, launch_bwd_one<R, true>(a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, g_probs,
+                                              g_voxels, g_grid, scale_partials, s));
+  } else {
+    DPC_DISPATCH_R(r, launch_bwd_one<R, false>(a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, nullptr,
+                                               nullptr, g_grid, scale_partials, s));
   }
-  DPC_DISPATCH_R(r,
-    cudaFuncSetAttribute(drc_blurz_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         200 * 1024);
-    drc_blurz_bwd_kernel<R><<<blocks, kRayThreads, smem, s>>>(
-        a.grid, a.scale, c, z_taps<R>(tz, kz, r), g_mask, g_depth, g_probs, g_voxels, g_grid,
-        a.scale ? scale_partials : nullptr));
   return check_launch("drc_blurz_bwd");
 }
 
 int launch_blur_z(const float *src, float *dst, int P, int Vz, int V, const float *tz, int kz,
                   cudaStream_t s) {
-  if ((V * V) % kRayThreads != 0) {
-    set_error("blur_z: V*V must be a multiple of %d", kRayThreads);
-    return DPC_ERR_ARG;
-  }
+  if (int e = check_ray_geometry(V)) return e;
   const int r = z_radius(tz, kz);
   const int blocks = P * V * V / kRayThreads;
   DPC_DISPATCH_R(r, blur_z_kernel<R><<<blocks, kRayThreads, 0, s>>>(src, dst, Vz, V * V,

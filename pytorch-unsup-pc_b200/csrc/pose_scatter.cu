@@ -217,9 +217,16 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
   }
 }
 
-// One warp per projection: sums the per-block partials in index order and
-// applies the quaternion-normalisation Jacobian
+// One warp per projection: lanes stride over the per-block partials, then a
+// fixed shuffle tree combines them (same order every run), and lane 0 applies
+// the quaternion-normalisation Jacobian
 //   dL/dq = (dL/dq^ - q^ (q^ . dL/dq^)) / |q|         (quaternion.py:119-121)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void finalize_kernel(PoseArgs a, const double *__restrict__ pose_partials,
                                 int pose_blocks, const float *__restrict__ scale_partials,
                                 int scale_blocks, float *__restrict__ g_quat,
@@ -227,27 +234,38 @@ __global__ void finalize_kernel(PoseArgs a, const double *__restrict__ pose_part
                                 float *__restrict__ g_scale) {
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
-  double v = 0;
-  if (lane < 8 && pose_partials) {
-    for (int k = 0; k < pose_blocks; ++k) v += pose_partials[((size_t)b * pose_blocks + k) * 8 + lane];
-  } else if (lane == 8 && scale_partials) {
-    for (int k = 0; k < scale_blocks; ++k) v += (double)scale_partials[(size_t)b * scale_blocks + k];
-  }
-  const double dw = __shfl_sync(0xffffffffu, v, 0), dx = __shfl_sync(0xffffffffu, v, 1),
-               dy = __shfl_sync(0xffffffffu, v, 2), dz = __shfl_sync(0xffffffffu, v, 3);
   if (pose_partials) {
-    if (lane == 0 && g_quat) {
-      const Quat q = load_quat(a.quat + 4 * b);
-      const double dot = q.w * dw + q.x * dx + q.y * dy + q.z * dz;
-      g_quat[4 * b] = (float)((dw - q.w * dot) * q.inv_norm);
-      g_quat[4 * b + 1] = (float)((dx - q.x * dot) * q.inv_norm);
-      g_quat[4 * b + 2] = (float)((dy - q.y * dot) * q.inv_norm);
-      g_quat[4 * b + 3] = (float)((dz - q.z * dot) * q.inv_norm);
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < pose_blocks; k += 32) {
+      const double *p = pose_partials + ((size_t)b * pose_blocks + k) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += p[i];
     }
-    if (lane >= 4 && lane < 7 && g_trans) g_trans[3 * b + lane - 4] = (float)v;
-    if (lane == 7 && g_focal) g_focal[b] = (float)v;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+      if (g_quat) {
+        const Quat q = load_quat(a.quat + 4 * b);
+        const double dot = q.w * acc[0] + q.x * acc[1] + q.y * acc[2] + q.z * acc[3];
+        g_quat[4 * b] = (float)((acc[0] - q.w * dot) * q.inv_norm);
+        g_quat[4 * b + 1] = (float)((acc[1] - q.x * dot) * q.inv_norm);
+        g_quat[4 * b + 2] = (float)((acc[2] - q.y * dot) * q.inv_norm);
+        g_quat[4 * b + 3] = (float)((acc[3] - q.z * dot) * q.inv_norm);
+      }
+      if (g_trans) {
+        g_trans[3 * b] = (float)acc[4];
+        g_trans[3 * b + 1] = (float)acc[5];
+        g_trans[3 * b + 2] = (float)acc[6];
+      }
+      if (g_focal) g_focal[b] = (float)acc[7];
+    }
   }
-  if (lane == 8 && g_scale && scale_partials) g_scale[b] = (float)v;
+  if (scale_partials && g_scale) {
+    double v = 0;
+    for (int k = lane; k < scale_blocks; k += 32) v += (double)scale_partials[(size_t)b * scale_blocks + k];
+    v = warp_sum(v);
+    if (lane == 0) g_scale[b] = (float)v;
+  }
 }
 
 // ---- launchers ---------------------------------------------------------------

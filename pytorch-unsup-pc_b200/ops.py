@@ -98,7 +98,7 @@ class ProjectFn(torch.autograd.Function):
     forward : memset + pose/scatter + blur XY (in place) + blur Z/DRC  (4 launches)
     backward: DRC reverse scan/blur Z adjoint + blur XY adjoint + gather/pose
               adjoint + finalize                                       (4 launches)
-    Saved for backward: the inputs, the XY-blurred grid and a 1-bit clamp mask.
+    Saved for backward: the inputs, the blurred grid and a 1-bit clamp mask.
     """
 
     @staticmethod
@@ -109,7 +109,7 @@ class ProjectFn(torch.autograd.Function):
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
         f32 = dict(dtype=torch.float32, device=dev)
         tr_pc = torch.empty(P, N, 3, **f32)
-        grid_xy = torch.empty(P, Vz, V, V, **f32)
+        grid_b = torch.empty(P, Vz, V, V, **f32)
         bits = torch.empty(P, Vz, V, V // 32, dtype=torch.int32, device=dev)
         mask = torch.empty(P, V, V, **f32)
         depth = torch.empty(P, V, V, **f32)
@@ -119,11 +119,11 @@ class ProjectFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = lib.dpc_project_fwd(
                 ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
-                _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), _ptr(grid_xy), _ptr(bits),
+                _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), _ptr(grid_b), _ptr(bits),
                 _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws), ws.numel(),
                 _stream(dev))
         _lib.check(st, "project_fwd")
-        ctx.save_for_backward(points, quat, trans, focal, scale, grid_xy, bits)
+        ctx.save_for_backward(points, quat, trans, focal, scale, grid_b, bits)
         ctx.params, ctx.taps = params, taps
         ctx.set_materialize_grads(False)
         return mask, depth, tr_pc, voxels, probs
@@ -131,7 +131,7 @@ class ProjectFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mask, g_depth, g_trpc, g_voxels, g_probs):
         lib = _lib.load()
-        points, quat, trans, focal, scale, grid_xy, bits = ctx.saved_tensors
+        points, quat, trans, focal, scale, grid_b, bits = ctx.saved_tensors
         params = ctx.params
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
@@ -151,7 +151,7 @@ class ProjectFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = lib.dpc_project_bwd(
                 ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
-                _ptr(scale), *_tap_args(ctx.taps), _ptr(grid_xy), _ptr(bits), _ptr(g_mask),
+                _ptr(scale), *_tap_args(ctx.taps), _ptr(grid_b), _ptr(bits), _ptr(g_mask),
                 _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid),
                 _ptr(g_points), _ptr(g_quat), _ptr(g_trans), _ptr(g_focal), _ptr(g_scale),
                 _ptr(ws), ws.numel(), _stream(dev))
