@@ -6,134 +6,194 @@
 // march, drc.cu), plus the clamp(raw,0,1) that precedes them (:198-201).
 //
 // One CTA owns one V x V plane of one projection, so neither pass needs a
-// halo: the zero padding lives in shared memory.  The plane is staged once
-// (coalesced float4 loads, clamp + raw<=1 bit mask fused on the way in), the
-// X pass writes its result transposed into a second shared tile, the Y pass
-// reads that tile and stores coalesced rows.  Because the whole plane is in
-// shared memory before the first store, src == dst is safe: the forward blurs
-// the occupancy grid in place and only a 1-bit-per-voxel mask survives for the
-// backward's clamp gate.
+// halo: the zero padding lives in shared memory.  Because the whole plane is
+// staged in shared memory before the first store, src == dst is safe: the
+// forward blurs the occupancy grid in place and only a 1-bit-per-voxel
+// raw<=1 mask survives for the backward's clamp gate.
 //
-// Inner loop: each thread produces 16 consecutive outputs from a 16+2R window
-// read with conflict-free LDS.128 (row stride = 4*odd floats); 16 independent
-// accumulators, taps as constant-bank FFMA operands: 336 FFMA per 9 LDS.128.
-// The backward (adjoint) is the same kernel: symmetric taps + zero padding
-// make each pass self-adjoint and the passes commute; the clamp gate is
-// applied on the final store.
+// Arithmetic is packed: every thread works on TWO independent lines at once
+// (two rows in the X pass, two columns in the Y pass) held as one 64-bit
+// register pair, so the 21-tap inner product issues as fma.rn.f32x2 (SASS
+// FFMA2) with the tap as a scalar operand -- half the issue slots of scalar
+// FFMA (ncu: the scalar version was issue-bound at 46 % FMA-pipe utilisation).
+//   tile A2[rowpair][x]  = (in[r][x],  in[r + RH/2][x])     x padded by R zeros
+//   tile B2[colpair][y]  = (bx[y][2c], bx[y][2c+1])         y padded by R zeros
+// Both tiles use a row stride of S pairs with S/2 odd, so the LDS.128 window
+// loads of 32 lanes on 32 consecutive lines are bank-conflict free.  Each
+// thread produces 16 outputs per line from a 16+2R window: 336 FFMA2 for
+// 18 LDS.128.  The Y pass stores coalesced 64-bit pairs.
+//
+// The backward (adjoint) is the same kernel: each zero-padded pass is the
+// transpose of itself with the taps reversed, the passes commute, and the
+// clamp gate is applied on the final store.
 #include "common.cuh"
 
 namespace dpc {
 
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 bx_pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void bx_unpack2(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 bx_fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 template <int V, int R>
 struct XYCfg {
-  static constexpr int J = 16;                    // outputs per thread per pass
-  static constexpr int W = J + 2 * R;             // window length
-  static constexpr int W4 = (W + 3) / 4;          // LDS.128 per window
-  static constexpr int RH = V < 64 ? V : 64;      // plane rows resident in tile A
-  static constexpr int S0 = V - J + 4 * W4;       // floats a row must hold
-  static constexpr int S = ((S0 / 4) % 2 == 1) ? S0 : S0 + 4;  // stride: 4*odd => no conflicts
-  static constexpr int TASKS2 = V * V / J;
-  static constexpr int THREADS = TASKS2 < 512 ? TASKS2 : 512;
-  static constexpr int MINB = (V == 128) ? 2 : (V == 64 ? 4 : 8);
-  static constexpr size_t SMEM = (size_t)(RH + V) * S * sizeof(float);
+  static constexpr int J = 16;                       // outputs per line per thread
+  static constexpr int W = J + 2 * R;                // window positions (even)
+  static constexpr int W2 = W / 2;                   // LDS.128 per window
+  static constexpr int RH = V < 64 ? V : 64;         // plane rows staged per X-pass round
+  static constexpr int S0 = V + 2 * R;               // positions a line must hold
+  static constexpr int S = (S0 % 4 == 2) ? S0 : S0 + 2;   // stride in pairs, S/2 odd
+  static constexpr int XTASKS = (RH / 2) * (V / J);
+  static constexpr int YTASKS = (V / 2) * (V / J);
+  static constexpr int THREADS = YTASKS < 128 ? YTASKS : (V == 128 ? 256 : 128);
+  static constexpr int FILL_ITEMS = (RH / 2) * (V / 4);
+  static constexpr size_t SMEM = (size_t)(RH / 2 + V / 2) * S * sizeof(float2);
   static_assert(V % 32 == 0, "V must be a multiple of 32");
-  static_assert((RH * V / 4) % THREADS == 0, "fill loop must be warp-uniform");
+  static_assert(R % 2 == 0 || true, "");
+  static_assert(FILL_ITEMS % THREADS == 0, "fill loop must be warp-uniform");
 };
 
-template <int R, int J, int W4>
-__device__ __forceinline__ void window_fma(const float *__restrict__ win_base,
-                                           const Taps<R> &taps, float (&acc)[J]) {
+// 16 packed outputs from a window of W pair-positions starting at `win`
+template <int R, int J, int W2>
+__device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, const u64 (&k2)[2 * R + 1],
+                                            u64 (&acc)[J]) {
 #pragma unroll
-  for (int j = 0; j < J; ++j) acc[j] = 0.f;
+  for (int j = 0; j < J; ++j) acc[j] = 0;
 #pragma unroll
-  for (int i = 0; i < W4; ++i) {
-    const float4 v4 = *reinterpret_cast<const float4 *>(win_base + 4 * i);
-    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  for (int i = 0; i < W2; ++i) {
+    const float4 v4 = *reinterpret_cast<const float4 *>(win + 2 * i);
+    const u64 vv[2] = {bx_pack2(v4.x, v4.y), bx_pack2(v4.z, v4.w)};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const int t = 4 * i + c - j;  // compile-time after unrolling
-        if (t >= 0 && t <= 2 * R) acc[j] = fmaf(taps.k[t], vv[c], acc[j]);
+        const int t = 2 * i + c - j;  // compile-time after unrolling
+        if (t >= 0 && t <= 2 * R) acc[j] = bx_fma2(k2[t], vv[c], acc[j]);
       }
     }
   }
 }
 
+__device__ __forceinline__ float4 clamp01(float4 v) {
+  v.x = fminf(fmaxf(v.x, 0.f), 1.f);
+  v.y = fminf(fmaxf(v.y, 0.f), 1.f);
+  v.z = fminf(fmaxf(v.z, 0.f), 1.f);
+  v.w = fminf(fmaxf(v.w, 0.f), 1.f);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t le1_nibble(float4 v) {
+  return (v.x <= 1.f ? 1u : 0u) | (v.y <= 1.f ? 2u : 0u) | (v.z <= 1.f ? 4u : 0u) |
+         (v.w <= 1.f ? 8u : 0u);
+}
+
 template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT>
-__global__ void __launch_bounds__(XYCfg<V, R>::THREADS, XYCfg<V, R>::MINB)
+__global__ void __launch_bounds__(XYCfg<V, R>::THREADS)
 blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                uint32_t *__restrict__ bits_out, const uint32_t *__restrict__ bits_in,
                const Taps<R> kx, const Taps<R> ky) {
   using C = XYCfg<V, R>;
-  extern __shared__ __align__(16) float smem[];
-  float *A = smem;                 // [RH][S]  input rows, x padded by R zeros
-  float *B = smem + C::RH * C::S;  // [V][S]   X-blurred, transposed: B[x][R + y]
+  constexpr int HALF = C::RH / 2;
+  extern __shared__ __align__(16) float2 smem2[];
+  float2 *A2 = smem2;                  // [RH/2][S]  (row r, row r + RH/2), x padded by R
+  float2 *B2 = smem2 + HALF * C::S;    // [V/2][S]   (col 2c, col 2c+1),    y padded by R
   const int tid = threadIdx.x;
   const size_t plane = blockIdx.x;
   const float *sp = src + plane * V * V;
 
   // zero both tiles once (the pads stay zero for the whole kernel)
-  for (int i = tid; i < (C::RH + V) * C::S / 4; i += C::THREADS)
-    reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < (HALF + V / 2) * C::S / 2; i += C::THREADS)
+    reinterpret_cast<float4 *>(smem2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  u64 k2[2 * R + 1];
+#pragma unroll
+  for (int t = 0; t < 2 * R + 1; ++t) k2[t] = bx_pack2(kx.k[t], kx.k[t]);
   __syncthreads();
 
 #pragma unroll 1
   for (int h = 0; h < V / C::RH; ++h) {
-    // ---- stage rows [h*RH, (h+1)*RH) ----
-    for (int i = tid; i < C::RH * V / 4; i += C::THREADS) {
-      const int row = i / (V / 4), c4 = i % (V / 4);
-      const int gy = h * C::RH + row;
-      float4 v = __ldg(reinterpret_cast<const float4 *>(sp + gy * V) + c4);
+    // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
+    for (int i = tid; i < C::FILL_ITEMS; i += C::THREADS) {
+      const int rp = i / (V / 4), c4 = i % (V / 4);
+      const int r0 = h * C::RH + rp, r1 = r0 + HALF;
+      float4 a = __ldg(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
+      float4 b = __ldg(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
       if (WRITE_BITS) {
-        uint32_t nib = (v.x <= 1.f ? 1u : 0u) | (v.y <= 1.f ? 2u : 0u) | (v.z <= 1.f ? 4u : 0u) |
-                       (v.w <= 1.f ? 8u : 0u);
-        nib <<= 4 * (tid & 7);
-        nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
-        nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-        nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
-        if ((tid & 7) == 0) bits_out[plane * (V * V / 32) + (gy * V + 4 * c4) / 32] = nib;
+        uint32_t na = le1_nibble(a) << (4 * (tid & 7)), nb = le1_nibble(b) << (4 * (tid & 7));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          na |= __shfl_xor_sync(0xffffffffu, na, o);
+          nb |= __shfl_xor_sync(0xffffffffu, nb, o);
+        }
+        if ((tid & 7) == 0) {
+          bits_out[plane * (V * V / 32) + (r0 * V + 4 * c4) / 32] = na;
+          bits_out[plane * (V * V / 32) + (r1 * V + 4 * c4) / 32] = nb;
+        }
       }
       if (CLAMP_IN) {
-        v.x = fminf(fmaxf(v.x, 0.f), 1.f);
-        v.y = fminf(fmaxf(v.y, 0.f), 1.f);
-        v.z = fminf(fmaxf(v.z, 0.f), 1.f);
-        v.w = fminf(fmaxf(v.w, 0.f), 1.f);
+        a = clamp01(a);
+        b = clamp01(b);
       }
-      float *a = A + row * C::S + R + 4 * c4;
+      float2 *d = A2 + rp * C::S + R + 4 * c4;
       if (R % 2 == 0) {
-        *reinterpret_cast<float2 *>(a) = make_float2(v.x, v.y);
-        *reinterpret_cast<float2 *>(a + 2) = make_float2(v.z, v.w);
+        *reinterpret_cast<float4 *>(d) = make_float4(a.x, b.x, a.y, b.y);
+        *reinterpret_cast<float4 *>(d + 2) = make_float4(a.z, b.z, a.w, b.w);
       } else {
-        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+        d[0] = make_float2(a.x, b.x);
+        d[1] = make_float2(a.y, b.y);
+        d[2] = make_float2(a.z, b.z);
+        d[3] = make_float2(a.w, b.w);
       }
     }
     __syncthreads();
-    // ---- X pass: lanes <-> 32 consecutive rows, one 16-wide x block ----
-    for (int task = tid; task < C::RH * V / C::J; task += C::THREADS) {
-      const int yl = task % C::RH, x0 = (task / C::RH) * C::J;
-      float acc[C::J];
-      window_fma<R, C::J, C::W4>(A + yl * C::S + x0, kx, acc);
-      float *b = B + x0 * C::S + R + h * C::RH + yl;
+    // ---- X pass: lanes <-> consecutive row pairs, one 16-wide x block ----
+    for (int task = tid; task < C::XTASKS; task += C::THREADS) {
+      const int rp = task % HALF, x0 = (task / HALF) * C::J;
+      u64 acc[C::J];
+      window_fma2<R, C::J, C::W2>(A2 + rp * C::S + x0, k2, acc);
+      // acc[j] = (out[r0][x0+j], out[r1][x0+j]) -> B2[(x0+j)/2][R + row] = (even col, odd col)
+      const int r0 = h * C::RH + rp, r1 = r0 + HALF;
+      float2 *b = B2 + (x0 / 2) * C::S + R;
 #pragma unroll
-      for (int j = 0; j < C::J; ++j) b[j * C::S] = acc[j];
+      for (int j = 0; j < C::J; j += 2) {
+        float e0, e1, o0, o1;
+        bx_unpack2(acc[j], e0, e1);       // column x0+j   : rows r0, r1
+        bx_unpack2(acc[j + 1], o0, o1);   // column x0+j+1 : rows r0, r1
+        b[(j / 2) * C::S + r0] = make_float2(e0, o0);
+        b[(j / 2) * C::S + r1] = make_float2(e1, o1);
+      }
     }
     __syncthreads();
   }
-  // ---- Y pass: lanes <-> 32 consecutive x, one 16-tall y block ----
+  // ---- Y pass: lanes <-> consecutive column pairs, one 16-tall y block ----
+#pragma unroll
+  for (int t = 0; t < 2 * R + 1; ++t) k2[t] = bx_pack2(ky.k[t], ky.k[t]);
   float *dp = dst + plane * V * V;
-  for (int task = tid; task < C::TASKS2; task += C::THREADS) {
-    const int x = task % V, y0 = (task / V) * C::J;
-    float acc[C::J];
-    window_fma<R, C::J, C::W4>(B + x * C::S + y0, ky, acc);
+  for (int task = tid; task < C::YTASKS; task += C::THREADS) {
+    const int cp = task % (V / 2), y0 = (task / (V / 2)) * C::J;
+    u64 acc[C::J];
+    window_fma2<R, C::J, C::W2>(B2 + cp * C::S + y0, k2, acc);
 #pragma unroll
     for (int j = 0; j < C::J; ++j) {
-      float o = acc[j];
+      float lo, hi;
+      bx_unpack2(acc[j], lo, hi);
       if (MASK_OUT) {
-        const uint32_t wbits = __ldg(bits_in + plane * (V * V / 32) + ((y0 + j) * V + x) / 32);
-        o = ((wbits >> (x & 31)) & 1u) ? o : 0.f;
+        const uint32_t wbits = __ldg(bits_in + plane * (V * V / 32) + ((y0 + j) * V + 2 * cp) / 32);
+        const uint32_t sh = (2 * cp) & 31;
+        lo = ((wbits >> sh) & 1u) ? lo : 0.f;
+        hi = ((wbits >> (sh + 1)) & 1u) ? hi : 0.f;
       }
-      dp[(y0 + j) * V + x] = o;
+      *reinterpret_cast<float2 *>(dp + (y0 + j) * V + 2 * cp) = make_float2(lo, hi);
     }
   }
 }

@@ -6,13 +6,21 @@
 // log-sum form with clip_val 'unity' padding), :114-129 (silhouette), :145-160
 // (expected depth) and the two Y flips point_cloud_to.py:239, 242.
 //
-// One thread owns one ray (b, y, x); a warp owns 32 consecutive x, so every
-// global access is a full 128-byte line.  The Z blur is a register ring of
-// 2R+1 values indexed at compile time (the z loop is unrolled by the ring
-// length) with the taps in uniform registers; each blurred value is consumed
-// by the ray march as soon as it is produced and written back IN PLACE over
-// the column it came from (an input is always loaded R steps before its slot
-// is overwritten), so the buffer the backward needs costs no extra memory.
+// One thread owns TWO x-adjacent rays (b, y, 2i) and (b, y, 2i+1); a warp owns
+// 64 consecutive x, so every global access is a 64-bit access in a fully used
+// 256-byte span.  The pair rides in one 64-bit register, so the Z blur -- the
+// bulk of the arithmetic -- issues as packed fma.rn.f32x2 (SASS FFMA2) with the
+// tap as a scalar uniform-register operand: half the issue slots of scalar
+// FFMA in kernels that ncu shows to be issue-bound, not pipe-bound.
+//
+// The blur is a register ring of L >= 2R+1 pairs indexed at compile time (the
+// z loop is unrolled by L; V is a template parameter so every address inside a
+// block is pointer + immediate).  The input for step z+R+D is loaded straight
+// into its ring slot at step z (D = L-(2R+1) steps of prefetch distance), each
+// blurred value is consumed by the ray march as soon as it is produced and is
+// written back IN PLACE over the column it came from (an input is always
+// loaded R+D steps before its slot is overwritten), so the tensor the backward
+// needs costs no extra memory.
 //
 //   vox_k = clamp(s * B_k, 0, 1)   B = blurZ(grid_xy)     v_k = clamp(vox_k, c, 1-c)
 //   p_k = e_k v_k T_k,  T_{k+1} = T_k (1 - v_k),  p_Z = e_Z T_Z,  e_0 = e_Z = exp(c)
@@ -28,7 +36,7 @@
 //   D_Z = a_Z e_Z,   D_k = a_k e_k v_k + (1 - v_k) D_{k+1},
 //   dL/dv_k = T_k (a_k e_k - D_{k+1}).
 // Sweep 1 (forward in z) copies the saved B column to shared memory
-// ([k][thread], conflict-free) and checkpoints T at every ring-length block;
+// ([k][thread], conflict-free) and checkpoints T at every block of L steps;
 // sweep 2 walks the blocks in reverse: it re-expands T inside the block from
 // the checkpoint, runs the D recursion downwards, applies the clip/clamp
 // gates and the scale, and pushes the result through the register ring to
@@ -40,12 +48,39 @@
 
 namespace dpc {
 
-constexpr int kRayThreads = 128;
+constexpr int kFwdThreads = 128;   // ray pairs per CTA (forward)
+constexpr int kBwdThreads = 64;    // ray pairs per CTA (backward: shared-memory bound)
 
-int drc_scale_partial_blocks(int V) { return V * V / kRayThreads; }
+int drc_scale_partial_blocks(int V) { return V * V / (2 * kBwdThreads); }
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// ring length for a tap radius: 2R+1 taps + a few steps of load-ahead
+template <int R> struct RingLen { static constexpr int L = 2 * R + 1 + 3; };
+template <> struct RingLen<0> { static constexpr int L = 8; };
+template <> struct RingLen<5> { static constexpr int L = 16; };
 
 struct RayConst {
-  int P, Vz, V, VV;
+  int P, Vz;
   float inv_z, depth0, max_depth, exp_clip;
   float lo_s, hi_s;   // clamp(s*B, 0, 1) bounds; +-inf when there is no scaling factor
   float lo_c, hi_c;   // DRC clip bounds;        +-inf for the product form
@@ -54,7 +89,7 @@ struct RayConst {
 
 static RayConst make_ray_const(const DrcArgs &a) {
   RayConst c;
-  c.P = a.P; c.Vz = a.Vz; c.V = a.V; c.VV = a.V * a.V;
+  c.P = a.P; c.Vz = a.Vz;
   c.inv_z = 1.0f / (float)a.Vz;
   c.depth0 = a.cam_dist - 0.5f;
   c.max_depth = a.max_depth;
@@ -68,128 +103,137 @@ static RayConst make_ray_const(const DrcArgs &a) {
   return c;
 }
 
-template <int R>
-__device__ __forceinline__ float ring_dot(const float (&ring)[2 * R + 1], const Taps<R> &taps,
-                                          int first /*compile-time*/, bool reversed) {
+// sum_t k[t] * ring[(first + t) % L]  (reversed: k[2R - t]), packed pairs
+template <int R, int L>
+__device__ __forceinline__ u64 ring_dot2(const u64 (&ring)[L], const u64 (&k2)[2 * R + 1],
+                                         int first /*compile-time*/, bool reversed) {
   constexpr int W = 2 * R + 1;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  u64 s0 = 0, s1 = 0, s2 = 0;   // bit pattern 0 == (0.f, 0.f)
 #pragma unroll
   for (int t = 0; t < W; ++t) {
-    const float v = ring[(first + t) % W];
-    const float k = reversed ? taps.k[W - 1 - t] : taps.k[t];
-    if (t % 3 == 0) s0 = fmaf(k, v, s0);
-    else if (t % 3 == 1) s1 = fmaf(k, v, s1);
-    else s2 = fmaf(k, v, s2);
+    const u64 v = ring[(first + t) % L];
+    const u64 k = reversed ? k2[W - 1 - t] : k2[t];
+    if (t % 3 == 0) s0 = fma2(k, v, s0);
+    else if (t % 3 == 1) s1 = fma2(k, v, s1);
+    else s2 = fma2(k, v, s2);
   }
-  return (s0 + s1) + s2;
+  if (W == 1) return s0;
+  return add2(add2(s0, s1), s2);
 }
 
-// Streams blurZ(col)_z for z = 0..Vz-1 to `sink(j, z, value)`; j is the
-// compile-time position inside the current block of W steps.
-template <int R, typename Sink>
-__device__ __forceinline__ void stream_blur_z(const float *col, int Vz, int VV,
-                                              const Taps<R> &taps, Sink &&sink) {
-  constexpr int W = 2 * R + 1;
-  if (R == 0) {
-#pragma unroll 8
-    for (int z = 0; z < Vz; ++z) {
-      sink(1, z, taps.k[0] * *col);
-      col += VV;
-    }
-    return;
-  }
-  float ring[W];
+template <int V>
+__device__ __forceinline__ void pair_index(const RayConst &c, int threads, int &b, int &yx,
+                                           int &out_idx) {
+  constexpr int VV = V * V;
+  const int pair = blockIdx.x * threads + threadIdx.x;
+  b = pair / (VV / 2);
+  yx = 2 * (pair - b * (VV / 2));            // even x
+  const int y = yx / V, x = yx - y * V;
+  const int yo = c.flip_y ? (V - 1 - y) : y;
+  out_idx = b * VV + yo * V + x;
+}
+
+// Streams the pair blurZ(col)_z, z = 0..Vz-1, to sink(j, z, lo, hi); j is the
+// compile-time position inside the current block of L steps.  SAVE writes the
+// blurred pair back over the input column (bs may alias col).
+template <int V, int R, bool SAVE, typename Sink>
+__device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int Vz,
+                                               const Taps<R> &taps, Sink &&sink) {
+  constexpr int W = 2 * R + 1, L = RingLen<R>::L, AHEAD = R + (L - W);   // load-ahead in steps
+  constexpr int VV = V * V;
+  u64 k2[W];
 #pragma unroll
-  for (int i = 0; i < W; ++i) ring[i] = 0.f;
-  const float *ld = col;
+  for (int t = 0; t < W; ++t) k2[t] = pack2(taps.k[t], taps.k[t]);
+  u64 ring[L];
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    ring[i] = (i < Vz) ? *ld : 0.f;
-    ld += VV;
-  }
+  for (int i = 0; i < L; ++i) ring[i] = 0;
+#pragma unroll
+  for (int i = 0; i < AHEAD; ++i)
+    if (i < Vz) ring[i] = *reinterpret_cast<const u64 *>(col + (size_t)i * VV);
 #pragma unroll 1
-  for (int z0 = 0; z0 < Vz; z0 += W) {
-    float nxt[W];
+  for (int z0 = 0; z0 < Vz; z0 += L) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      nxt[j] = (z0 + j + R < Vz) ? *ld : 0.f;
-      ld += VV;
-    }
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
+    for (int j = 0; j < L; ++j) {
       const int z = z0 + j;
       if (z < Vz) {
-        ring[(j + R) % W] = nxt[j];
-        sink(j, z, ring_dot<R>(ring, taps, (j + R + 1) % W, false));
+        ring[(j + AHEAD) % L] =
+            (z + AHEAD < Vz) ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
+        const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
+        if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = b2;
+        float lo, hi;
+        unpack2(b2, lo, hi);
+        sink(j, z, lo, hi);
       }
     }
+    col += (size_t)L * VV;
+    if (SAVE) bs += (size_t)L * VV;
   }
-}
-
-__device__ __forceinline__ void ray_index(const RayConst &c, int &b, int &yx, int &out_idx) {
-  const int ray = blockIdx.x * kRayThreads + threadIdx.x;
-  b = ray / c.VV;
-  yx = ray - b * c.VV;
-  const int y = yx / c.V, x = yx - y * c.V;
-  const int yo = c.flip_y ? (c.V - 1 - y) : y;
-  out_idx = b * c.VV + yo * c.V + x;
 }
 
 // EXTRA: the optional voxels / probs outputs exist.  `grid` and `bsave` may
 // alias (in-place save), so neither is __restrict__.
-template <int R, bool EXTRA>
-__global__ void __launch_bounds__(kRayThreads)
+template <int V, int R, bool EXTRA, bool SAVE>
+__global__ void __launch_bounds__(kFwdThreads)
 blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayConst c,
                      const Taps<R> kz, float *bsave, float *__restrict__ mask,
                      float *__restrict__ depth, float *__restrict__ voxels,
                      float *__restrict__ probs) {
+  constexpr int VV = V * V;
   int b, yx, oi;
-  ray_index(c, b, yx, oi);
-  const size_t col0 = (size_t)b * c.Vz * c.VV + yx;
+  pair_index<V>(c, kFwdThreads, b, yx, oi);
+  const size_t col0 = (size_t)b * c.Vz * VV + yx;
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
-  float T = 1.f, m = 0.f, d = 0.f, kf = 0.f;
-  float *bs = bsave ? bsave + col0 : nullptr;
+  float T[2] = {1.f, 1.f}, m[2] = {0.f, 0.f}, d[2] = {0.f, 0.f};
+  float kf = 0.f;
   float *vx = (EXTRA && voxels) ? voxels + col0 : nullptr;
   float *pr = (EXTRA && probs) ? probs + oi : nullptr;
-  const size_t pstride = (size_t)c.P * c.VV;
-  stream_blur_z<R>(grid + col0, c.Vz, c.VV, kz, [&](int j, int z, float bz) {
-    if (bs) { *bs = bz; bs += c.VV; }
-    const float vox = fminf(fmaxf(s * bz, c.lo_s), c.hi_s);
-    const float v = fminf(fmaxf(vox, c.lo_c), c.hi_c);
-    float p = v * T;
-    if ((R == 0 || j == 0) && z == 0) p *= c.exp_clip;   // only block position 0 can be z == 0
-    if (EXTRA) {
-      if (vx) { *vx = vox; vx += c.VV; }
-      if (pr) { *pr = p; pr += pstride; }
-    }
-    m += p;
-    d = fmaf(fmaf(kf, c.inv_z, c.depth0), p, d);
+  const size_t pstride = (size_t)c.P * VV;
+  stream_blur_z2<V, R, SAVE>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
+                             [&](int j, int z, float b0, float b1) {
+    const float psi = fmaf(kf, c.inv_z, c.depth0);
     kf += 1.f;
-    T *= (1.f - v);
+    const float bz[2] = {b0, b1};
+    float vox[2], p[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      vox[h] = fminf(fmaxf(s * bz[h], c.lo_s), c.hi_s);
+      const float v = fminf(fmaxf(vox[h], c.lo_c), c.hi_c);
+      p[h] = v * T[h];
+      if (j == 0 && z == 0) p[h] *= c.exp_clip;   // only block position 0 can be z == 0
+      m[h] += p[h];
+      d[h] = fmaf(psi, p[h], d[h]);
+      T[h] *= (1.f - v);
+    }
+    if (EXTRA) {
+      if (vx) { *reinterpret_cast<float2 *>(vx) = make_float2(vox[0], vox[1]); vx += VV; }
+      if (pr) { *reinterpret_cast<float2 *>(pr) = make_float2(p[0], p[1]); pr += pstride; }
+    }
   });
-  const float pz = c.exp_clip * T;
-  if (EXTRA && pr) *pr = pz;
-  mask[oi] = m;
-  if (depth) depth[oi] = fmaf(c.max_depth, pz, d);
+  const float pz0 = c.exp_clip * T[0], pz1 = c.exp_clip * T[1];
+  if (EXTRA && pr) *reinterpret_cast<float2 *>(pr) = make_float2(pz0, pz1);
+  *reinterpret_cast<float2 *>(mask + oi) = make_float2(m[0], m[1]);
+  if (depth)
+    *reinterpret_cast<float2 *>(depth + oi) =
+        make_float2(fmaf(c.max_depth, pz0, d[0]), fmaf(c.max_depth, pz1, d[1]));
 }
 
-template <int R, bool EXTRA>
-__global__ void __launch_bounds__(kRayThreads)
+template <int V, int R, bool EXTRA>
+__global__ void __launch_bounds__(kBwdThreads)
 drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ scale, RayConst c,
                      const Taps<R> kz, const float *__restrict__ g_mask,
                      const float *__restrict__ g_depth, const float *__restrict__ g_probs,
                      const float *__restrict__ g_voxels, float *__restrict__ g_grid,
                      float *__restrict__ scale_partials) {
-  constexpr int W = 2 * R + 1;
-  constexpr int BL = (R == 0) ? 16 : W;   // block length, a multiple of the ring length
-  extern __shared__ float sm[];
-  float *sB = sm + threadIdx.x;                        // [Vz][threads]     saved blurZ value
-  float *sC = sm + c.Vz * kRayThreads + threadIdx.x;   // [nblk][threads]   T at block starts
+  constexpr int W = 2 * R + 1, L = RingLen<R>::L;   // block length == ring length
+  constexpr int VV = V * V;
+  extern __shared__ float2 sm2[];
+  float2 *sB = sm2 + threadIdx.x;                        // [Vz][threads]    saved blurZ pair
+  float2 *sC = sm2 + c.Vz * kBwdThreads + threadIdx.x;   // [nblk][threads]  T at block starts
   int b, yx, oi;
-  ray_index(c, b, yx, oi);
-  const size_t col0 = (size_t)b * c.Vz * c.VV + yx;
+  pair_index<V>(c, kBwdThreads, b, yx, oi);
+  const size_t col0 = (size_t)b * c.Vz * VV + yx;
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
-  const int nblk = (c.Vz + BL - 1) / BL;
+  const int nblk = (c.Vz + L - 1) / L;
 
   auto occupancy = [&](float bz, float &sb, float &vox) -> float {
     sb = s * bz;
@@ -197,108 +241,125 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
     return fminf(fmaxf(vox, c.lo_c), c.hi_c);
   };
 
-  // ---- sweep 1: stage the column, checkpoint the transmittance ----
+  // ---- sweep 1: stage the column pair, checkpoint the transmittance ----
   {
     const float *ld = bgrid + col0;
-    float T = 1.f;
+    float T0 = 1.f, T1 = 1.f;
 #pragma unroll 1
     for (int bi = 0; bi < nblk; ++bi) {
-      sC[bi * kRayThreads] = T;
-      float vals[BL];
+      sC[bi * kBwdThreads] = make_float2(T0, T1);
+      float2 vals[L];
 #pragma unroll
-      for (int j = 0; j < BL; ++j) {
-        vals[j] = (bi * BL + j < c.Vz) ? __ldg(ld) : 0.f;
-        ld += c.VV;
-      }
+      for (int j = 0; j < L; ++j)
+        vals[j] = (bi * L + j < c.Vz) ? __ldg(reinterpret_cast<const float2 *>(ld + (size_t)j * VV))
+                                      : make_float2(0.f, 0.f);
+      ld += (size_t)L * VV;
 #pragma unroll
-      for (int j = 0; j < BL; ++j) {
-        const int z = bi * BL + j;
+      for (int j = 0; j < L; ++j) {
+        const int z = bi * L + j;
         if (z < c.Vz) {
-          sB[z * kRayThreads] = vals[j];
+          sB[z * kBwdThreads] = vals[j];
           float sb, vox;
-          T *= (1.f - occupancy(vals[j], sb, vox));
+          T0 *= (1.f - occupancy(vals[j].x, sb, vox));
+          T1 *= (1.f - occupancy(vals[j].y, sb, vox));
         }
       }
     }
   }
   // ---- sweep 2: reverse scan + Z-blur adjoint ----
-  const float gm = g_mask ? __ldg(g_mask + oi) : 0.f;
-  const float gd = g_depth ? __ldg(g_depth + oi) : 0.f;
-  const size_t pstride = (size_t)c.P * c.VV;
-  float D = c.max_depth * gd;
-  if (EXTRA && g_probs) D += __ldg(g_probs + (size_t)c.Vz * pstride + oi);
-  D *= c.exp_clip;
+  const float2 gm = g_mask ? __ldg(reinterpret_cast<const float2 *>(g_mask + oi)) : make_float2(0.f, 0.f);
+  const float2 gd = g_depth ? __ldg(reinterpret_cast<const float2 *>(g_depth + oi)) : make_float2(0.f, 0.f);
+  const size_t pstride = (size_t)c.P * VV;
+  float D[2] = {c.max_depth * gd.x, c.max_depth * gd.y};
+  if (EXTRA && g_probs) {
+    const float2 gz = __ldg(reinterpret_cast<const float2 *>(g_probs + (size_t)c.Vz * pstride + oi));
+    D[0] += gz.x;
+    D[1] += gz.y;
+  }
+  D[0] *= c.exp_clip;
+  D[1] *= c.exp_clip;
   float ds = 0.f;
-  float ring[W];
+  u64 k2[W];
 #pragma unroll
-  for (int i = 0; i < W; ++i) ring[i] = 0.f;
+  for (int t = 0; t < W; ++t) k2[t] = pack2(kz.k[t], kz.k[t]);
+  u64 ring[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) ring[i] = 0;
 
 #pragma unroll 1
   for (int bi = nblk - 1; bi >= 0; --bi) {
-    const int z0 = bi * BL;
+    const int z0 = bi * L;
     // re-expand T_k inside the block from its checkpoint
-    float tseg[BL];
+    float2 tseg[L];
     {
-      float T = sC[bi * kRayThreads];
+      float2 T = sC[bi * kBwdThreads];
 #pragma unroll
-      for (int j = 0; j < BL; ++j) {
+      for (int j = 0; j < L; ++j) {
         tseg[j] = T;
         if (z0 + j < c.Vz) {
+          const float2 bz = sB[(z0 + j) * kBwdThreads];
           float sb, vox;
-          T *= (1.f - occupancy(sB[(z0 + j) * kRayThreads], sb, vox));
+          T.x *= (1.f - occupancy(bz.x, sb, vox));
+          T.y *= (1.f - occupancy(bz.y, sb, vox));
         }
       }
     }
-    // pointers at k = z0 + BL - 1 (outputs at z = k + R); they walk downwards
-    float *gout = g_grid + col0 + (ptrdiff_t)(z0 + BL - 1 + R) * c.VV;
-    const float *gpr =
-        (EXTRA && g_probs) ? g_probs + (ptrdiff_t)(z0 + BL - 1) * (ptrdiff_t)pstride + oi : nullptr;
-    const float *gvx =
-        (EXTRA && g_voxels) ? g_voxels + col0 + (ptrdiff_t)(z0 + BL - 1) * c.VV : nullptr;
-    float kf = (float)(z0 + BL - 1);
+    // block-base pointers; inside the block every offset is an immediate
+    float *gout = g_grid + col0 + (size_t)(z0 + R) * VV;               // row z = k + R at j = 0
+    const float *gpr = (EXTRA && g_probs) ? g_probs + (size_t)z0 * pstride + oi : nullptr;
+    const float *gvx = (EXTRA && g_voxels) ? g_voxels + col0 + (size_t)z0 * VV : nullptr;
+    const float kf0 = (float)z0;
 #pragma unroll
-    for (int j = BL - 1; j >= 0; --j) {
+    for (int j = L - 1; j >= 0; --j) {
       const int k = z0 + j;
-      float gB = 0.f;
+      float gB[2] = {0.f, 0.f};
       if (k < c.Vz) {
-        const float bz = sB[k * kRayThreads];
-        float sb, vox;
-        const float v = occupancy(bz, sb, vox);
-        float a = fmaf(fmaf(kf, c.inv_z, c.depth0), gd, gm);
-        if (EXTRA && gpr) a += __ldg(gpr);
-        if (j == 0 && k == 0) a *= c.exp_clip;
-        float gv = tseg[j] * (a - D);
-        D = fmaf(a, v, (1.f - v) * D);
-        gv = (vox >= c.lo_c && vox <= c.hi_c) ? gv : 0.f;
-        if (EXTRA && gvx) gv += __ldg(gvx);
-        gv = (sb >= c.lo_s && sb <= c.hi_s) ? gv : 0.f;
-        ds = fmaf(gv, bz, ds);
-        gB = gv * s;
+        const float2 bz2 = sB[k * kBwdThreads];
+        const float bz[2] = {bz2.x, bz2.y}, Tk[2] = {tseg[j].x, tseg[j].y};
+        const float gmh[2] = {gm.x, gm.y}, gdh[2] = {gd.x, gd.y};
+        const float psi = fmaf(kf0 + (float)j, c.inv_z, c.depth0);
+        float2 gp2 = make_float2(0.f, 0.f), gv2 = make_float2(0.f, 0.f);
+        if (EXTRA) {
+          if (gpr) gp2 = __ldg(reinterpret_cast<const float2 *>(gpr + (size_t)j * pstride));
+          if (gvx) gv2 = __ldg(reinterpret_cast<const float2 *>(gvx + (size_t)j * VV));
+        }
+        const float gph[2] = {gp2.x, gp2.y}, gvh[2] = {gv2.x, gv2.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float sb, vox;
+          const float v = occupancy(bz[h], sb, vox);
+          float a = fmaf(psi, gdh[h], gmh[h]);
+          if (EXTRA) a += gph[h];
+          if (j == 0 && k == 0) a *= c.exp_clip;
+          float gv = Tk[h] * (a - D[h]);
+          D[h] = fmaf(a, v, (1.f - v) * D[h]);
+          gv = (vox >= c.lo_c && vox <= c.hi_c) ? gv : 0.f;
+          if (EXTRA) gv += gvh[h];
+          gv = (sb >= c.lo_s && sb <= c.hi_s) ? gv : 0.f;
+          ds = fmaf(gv, bz[h], ds);
+          gB[h] = gv * s;
+        }
       }
-      ring[j % W] = gB;
-      // out[z] = sum_t kz[2R-t] * in[k + t], z = k + R   (adjoint = reversed taps)
-      if (k + R < c.Vz) *gout = ring_dot<R>(ring, kz, j % W, true);
-      gout -= c.VV;
-      if (EXTRA) {
-        if (gpr) gpr -= pstride;
-        if (gvx) gvx -= c.VV;
-      }
-      kf -= 1.f;
+      ring[j] = pack2(gB[0], gB[1]);
+      // out[z] = sum_t kz[2R-t] * in[k + t], z = k + R   (adjoint = reversed taps);
+      // in[k + t] sits in slot (j + t) % L
+      if (k + R < c.Vz)
+        *reinterpret_cast<u64 *>(gout + (size_t)j * VV) = ring_dot2<R, L>(ring, k2, j, true);
     }
   }
   if (R > 0) {
     // flush: inputs k = -1 .. -R are zero; they complete the outputs z = R-1 .. 0
-    float *gout = g_grid + col0 + (ptrdiff_t)(R - 1) * c.VV;
+    float *gout = g_grid + col0;
 #pragma unroll
-    for (int j = BL - 1; j >= BL - R; --j) {
-      ring[j % W] = 0.f;
-      if (j - BL + R < c.Vz) *gout = ring_dot<R>(ring, kz, j % W, true);
-      gout -= c.VV;
+    for (int j = L - 1; j >= L - R; --j) {
+      ring[j] = 0;
+      const int z = j - L + R;
+      if (z < c.Vz) *reinterpret_cast<u64 *>(gout + (size_t)z * VV) = ring_dot2<R, L>(ring, k2, j, true);
     }
   }
   // ---- dL/dscale: fixed-order block reduction ----
   if (scale_partials) {
-    __shared__ float red[kRayThreads / 32];
+    __shared__ float red[kBwdThreads / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ds += __shfl_down_sync(0xffffffffu, ds, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
@@ -306,29 +367,26 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
     if (threadIdx.x == 0) {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kRayThreads / 32; ++w) v += red[w];
+      for (int w = 0; w < kBwdThreads / 32; ++w) v += red[w];
       scale_partials[blockIdx.x] = v;  // blocks are projection-major
     }
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(kRayThreads)
-blur_z_kernel(const float *src, float *dst, int Vz, int VV, const Taps<R> kz) {
-  const int ray = blockIdx.x * kRayThreads + threadIdx.x;
-  const int b = ray / VV, yx = ray - b * VV;
-  const float *col = src + (size_t)b * Vz * VV + yx;
-  float *out = dst + (size_t)b * Vz * VV + yx;
-  stream_blur_z<R>(col, Vz, VV, kz, [&](int, int, float bz) {
-    *out = bz;
-    out += VV;
-  });
+template <int V, int R>
+__global__ void __launch_bounds__(kFwdThreads)
+blur_z_kernel(const float *src, float *dst, int Vz, const Taps<R> kz) {
+  constexpr int VV = V * V;
+  const int pair = blockIdx.x * kFwdThreads + threadIdx.x;
+  const int b = pair / (VV / 2), yx = 2 * (pair - b * (VV / 2));
+  const size_t col0 = (size_t)b * Vz * VV + yx;
+  stream_blur_z2<V, R, true>(src + col0, dst + col0, Vz, kz, [](int, int, float, float) {});
 }
 
-__global__ void __launch_bounds__(kRayThreads)
+__global__ void __launch_bounds__(128)
 depth_from_probs_kernel(const float *__restrict__ probs, float *__restrict__ depth, int P, int Vz,
                         int VV, float inv_z, float depth0, float max_depth) {
-  const int i = blockIdx.x * kRayThreads + threadIdx.x;
+  const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= P * VV) return;
   const size_t stride = (size_t)P * VV;
   float d = 0.f;
@@ -358,14 +416,6 @@ static Taps<R> z_taps(const float *tz, int kz, int r) {
   return make_taps<R>(tz + off, 2 * r + 1);
 }
 
-static int check_ray_geometry(int V) {
-  if ((V * V) % kRayThreads != 0) {
-    set_error("drc: V*V must be a multiple of %d", kRayThreads);
-    return DPC_ERR_ARG;
-  }
-  return 0;
-}
-
 #define DPC_DISPATCH_R(r, ...)                                            \
   do {                                                                    \
     if (r == 0) { constexpr int R = 0; __VA_ARGS__; }                     \
@@ -374,41 +424,52 @@ static int check_ray_geometry(int V) {
     else if (r <= 10) { constexpr int R = 10; __VA_ARGS__; }              \
     else { set_error("z tap radius %d > 10 unsupported", r); return DPC_ERR_ARG; } \
   } while (0)
+#define DPC_DISPATCH_V(v, ...)                                            \
+  do {                                                                    \
+    if (v == 32) { constexpr int V = 32; __VA_ARGS__; }                   \
+    else if (v == 64) { constexpr int V = 64; __VA_ARGS__; }              \
+    else if (v == 128) { constexpr int V = 128; __VA_ARGS__; }            \
+    else { set_error("vox_size %d unsupported (32, 64, 128)", v); return DPC_ERR_ARG; } \
+  } while (0)
+
+template <int V, int R>
+static void launch_fwd_vr(const DrcArgs &a, const RayConst &c, const Taps<R> &taps, float *bsave,
+                          float *mask, float *depth, float *voxels, float *probs, cudaStream_t s) {
+  const int blocks = a.P * (V * V / 2) / kFwdThreads;
+  const bool extra = voxels || probs;
+#define DPC_FWD(EX, SV)                                                                 \
+  blurz_drc_fwd_kernel<V, R, EX, SV><<<blocks, kFwdThreads, 0, s>>>(a.grid, a.scale, c, taps, \
+                                                                    bsave, mask, depth, voxels, probs)
+  if (bsave) { if (extra) DPC_FWD(true, true); else DPC_FWD(false, true); }
+  else { if (extra) DPC_FWD(true, false); else DPC_FWD(false, false); }
+#undef DPC_FWD
+}
 
 int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave, float *mask,
                          float *depth, float *voxels, float *probs, cudaStream_t s) {
-  if (int e = check_ray_geometry(a.V)) return e;
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
-  const int blocks = a.P * a.V * a.V / kRayThreads;
-  if (voxels || probs) {
-    DPC_DISPATCH_R(r, blurz_drc_fwd_kernel<R, true><<<blocks, kRayThreads, 0, s>>>(
-                          a.grid, a.scale, c, z_taps<R>(tz, kz, r), bsave, mask, depth, voxels,
-                          probs));
-  } else {
-    DPC_DISPATCH_R(r, blurz_drc_fwd_kernel<R, false><<<blocks, kRayThreads, 0, s>>>(
-                          a.grid, a.scale, c, z_taps<R>(tz, kz, r), bsave, mask, depth, nullptr,
-                          nullptr));
-  }
+  DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_fwd_vr<V, R>(a, c, z_taps<R>(tz, kz, r), bsave, mask,
+                                                           depth, voxels, probs, s)));
   return check_launch("blurz_drc_fwd");
 }
 
-template <int R, bool EXTRA>
+template <int V, int R, bool EXTRA>
 static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
                            const float *g_mask, const float *g_depth, const float *g_probs,
                            const float *g_voxels, float *g_grid, float *scale_partials,
                            cudaStream_t s) {
-  constexpr int BL = (R == 0) ? 16 : 2 * R + 1;
-  const int nblk = (a.Vz + BL - 1) / BL;
-  const size_t smem = (size_t)(a.Vz + nblk) * kRayThreads * sizeof(float);
+  constexpr int L = RingLen<R>::L;
+  const int nblk = (a.Vz + L - 1) / L;
+  const size_t smem = (size_t)(a.Vz + nblk) * kBwdThreads * sizeof(float2);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(drc_blurz_bwd_kernel<R, EXTRA>,
+    cudaFuncSetAttribute(drc_blurz_bwd_kernel<V, R, EXTRA>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;
   }
-  const int blocks = a.P * a.V * a.V / kRayThreads;
-  drc_blurz_bwd_kernel<R, EXTRA><<<blocks, kRayThreads, smem, s>>>(
+  const int blocks = a.P * (V * V / 2) / kBwdThreads;
+  drc_blurz_bwd_kernel<V, R, EXTRA><<<blocks, kBwdThreads, smem, s>>>(
       a.grid, a.scale, c, taps, g_mask, g_depth, g_probs, g_voxels, g_grid,
       a.scale ? scale_partials : nullptr);
 }
@@ -416,34 +477,35 @@ static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &t
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
                          float *g_grid, float *scale_partials, cudaStream_t s) {
-  if (int e = check_ray_geometry(a.V)) return e;
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
   if (g_probs || g_voxels) {
-    DPC_DISPATCH_R(r, launch_bwd_one<R, true>(a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, g_probs,
-                                              g_voxels, g_grid, scale_partials, s));
+    DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_one<V, R, true>(
+                                              a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, g_probs,
+                                              g_voxels, g_grid, scale_partials, s)));
   } else {
-    DPC_DISPATCH_R(r, launch_bwd_one<R, false>(a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, nullptr,
-                                               nullptr, g_grid, scale_partials, s));
+    DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_one<V, R, false>(
+                                              a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, nullptr,
+                                              nullptr, g_grid, scale_partials, s)));
   }
   return check_launch("drc_blurz_bwd");
 }
 
 int launch_blur_z(const float *src, float *dst, int P, int Vz, int V, const float *tz, int kz,
                   cudaStream_t s) {
-  if (int e = check_ray_geometry(V)) return e;
   const int r = z_radius(tz, kz);
-  const int blocks = P * V * V / kRayThreads;
-  DPC_DISPATCH_R(r, blur_z_kernel<R><<<blocks, kRayThreads, 0, s>>>(src, dst, Vz, V * V,
-                                                                    z_taps<R>(tz, kz, r)));
+  DPC_DISPATCH_V(V, DPC_DISPATCH_R(r, blur_z_kernel<V, R><<<P * (V * V / 2) / kFwdThreads,
+                                                          kFwdThreads, 0, s>>>(
+                                          src, dst, Vz, z_taps<R>(tz, kz, r))));
   return check_launch("blur_z");
 }
 
 int launch_depth_from_probs(const float *probs, float *depth, int P, int Vz, int V,
                             float cam_dist, float max_depth, cudaStream_t s) {
   const int n = P * V * V;
-  depth_from_probs_kernel<<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, s>>>(
-      probs, depth, P, Vz, V * V, 1.0f / (float)Vz, cam_dist - 0.5f, max_depth);
+  depth_from_probs_kernel<<<(n + 127) / 128, 128, 0, s>>>(probs, depth, P, Vz, V * V,
+                                                          1.0f / (float)Vz, cam_dist - 0.5f,
+                                                          max_depth);
   return check_launch("depth_from_probs");
 }
 
