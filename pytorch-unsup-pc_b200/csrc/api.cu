@@ -2,6 +2,7 @@
 // stream-ordered launch sequences.  No allocation, no host synchronisation.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -122,7 +123,7 @@ static PoseArgs pose_args(const dpc_params *p, const float *points, const float 
 static DrcArgs drc_args(const dpc_params *p, const float *grid, const float *scale) {
   DrcArgs a;
   a.grid = grid; a.scale = scale;
-  a.P = p->P; a.Vz = p->Vz; a.V = p->V;
+  a.P = p->P; a.P_total = p->P; a.Vz = p->Vz; a.V = p->V;
   a.cam_dist = (float)p->camera_distance;
   a.max_depth = (float)p->max_depth;
   a.clip = (float)p->drc_clip;
@@ -244,6 +245,95 @@ int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, float *g
                                      (cudaStream_t)stream);
 }
 
+// ---- optional chunked two-stream pipeline (experiment, off by default) -------
+// Idea: run the batch as chunks of `chunk` projections on two internal streams
+// so that one chunk's kernels overlap the other's and a chunk's grid stays in
+// the 126 MB L2 between the kernel that writes it and the kernels that read it.
+// Measured on B200 at P=64, 64^3 (CUDA-graph replay, so no host launch cost):
+// 1 chunk 218 us/step, 2 chunks 223, 4 chunks 264, 8 chunks 333 -- the smaller
+// grids lose more to wave quantisation and per-kernel ramp than they gain, so
+// the default is ONE pass over the whole batch on the caller's stream.
+// DPC_CHUNK=<n> (env) re-enables chunking for experiments.
+struct Pipeline {
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  bool ready = false;
+};
+static thread_local Pipeline tl_pipe[64];
+static thread_local bool tl_force_single = false;
+
+static Pipeline *get_pipeline() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Pipeline &pl = tl_pipe[dev];
+  if (!pl.ready) {
+    for (int i = 0; i < 2; ++i) {
+      if (cudaStreamCreateWithFlags(&pl.side[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&pl.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&pl.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    pl.ready = true;
+  }
+  return &pl;
+}
+
+static int chunk_size(const dpc_params *p) {
+  if (tl_force_single) return p->P;
+  static int env_chunk = -1;
+  if (env_chunk < 0) {
+    const char *e = getenv("DPC_CHUNK");
+    env_chunk = e ? atoi(e) : 0;
+  }
+  if (env_chunk > 0) return env_chunk;
+  return p->P;
+}
+
+struct FwdPtrs {
+  const float *points, *quat, *trans, *focal, *scale;
+  float *tr_pc, *grid_b; uint32_t *bits; float *mask, *depth, *voxels, *probs;
+};
+
+// projections [b0, b0+n) of the forward pass on stream s
+static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &q, const float *tx,
+                             int kx, const float *ty, int ky, const float *tz, int kz,
+                             int scatter_mode, const Workspace &w, cudaStream_t s) {
+  dpc_params sp = *p;
+  sp.P = n;
+  const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V, I = (size_t)p->V * p->V;
+  const PoseArgs pa = pose_args(&sp, q.points + b0 * N3, q.quat + b0 * 4,
+                                q.trans ? q.trans + b0 * 3 : nullptr,
+                                q.focal ? q.focal + b0 : nullptr);
+  float *grid = q.grid_b + b0 * G;
+  float *tr_pc = q.tr_pc ? q.tr_pc + b0 * N3 : nullptr;
+  stage_mark(s);
+  if (scatter_mode == DPC_SCATTER_SORTED) {
+    stage_mark(s);
+    DPC_TRY(launch_scatter_sorted(&pa, nullptr, n, p->N, p->Vz, p->V, tr_pc, grid,
+                                  (uint32_t *)w.sorted + (size_t)2 * b0 * p->N,
+                                  sorted_workspace_bytes(n, p->N, p->Vz, p->V), s));
+  } else {
+    if (cudaMemsetAsync(grid, 0, (size_t)n * G * sizeof(float), s) != cudaSuccess)
+      return check_launch("memset");
+    stage_mark(s);
+    DPC_TRY(launch_pose_scatter(pa, tr_pc, grid, s));
+  }
+  // clamp(raw,0,1) + raw<=1 mask + blur X + blur Y, in place (identity taps when kernel=None)
+  BlurXYArgs b;
+  b.src = grid; b.dst = grid; b.bits_out = q.bits + b0 * (G / 32); b.bits_in = nullptr;
+  b.planes = n * p->Vz; b.V = p->V; b.clamp_in = true;
+  stage_mark(s);
+  DPC_TRY(launch_blur_xy(b, tx, kx, ty, ky, s));
+  stage_mark(s);
+  // blur Z + scale + clip + DRC; the blurred occupancy overwrites grid in place (saved for bwd)
+  DrcArgs da = drc_args(&sp, grid, q.scale ? q.scale + b0 : nullptr);
+  da.P_total = p->P;
+  DPC_TRY(launch_blurz_drc_fwd(da, tz, kz, grid, q.mask + b0 * I, q.depth ? q.depth + b0 * I : nullptr,
+                               q.voxels ? q.voxels + b0 * G : nullptr,
+                               q.probs ? q.probs + b0 * I : nullptr, s));
+  stage_mark(s);
+  return DPC_OK;
+}
+
 int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
                     const float *ty, int ky, const float *tz, int kz, int scatter_mode,
@@ -255,33 +345,71 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
   DPC_REQUIRE(mask);
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
   DPC_TRY(check_taps(tz, kz, "taps_z"));
-  cudaStream_t s = (cudaStream_t)stream;
-  const PoseArgs pa = pose_args(p, points, quat, trans, focal);
-  stage_mark(s);
-  if (scatter_mode == DPC_SCATTER_SORTED) {
-    DPC_TRY(check_ws(p, workspace, workspace_bytes));
-    const Workspace w = carve(p, workspace);
-    stage_mark(s);
-    DPC_TRY(launch_scatter_sorted(&pa, nullptr, p->P, p->N, p->Vz, p->V, tr_pc, grid_b, w.sorted,
-                                  w.sorted_bytes, s));
-  } else if (scatter_mode == DPC_SCATTER_ATOMIC) {
-    if (cudaMemsetAsync(grid_b, 0, grid_bytes(p), s) != cudaSuccess) return check_launch("memset");
-    stage_mark(s);
-    DPC_TRY(launch_pose_scatter(pa, tr_pc, grid_b, s));
-  } else {
+  if (scatter_mode != DPC_SCATTER_SORTED && scatter_mode != DPC_SCATTER_ATOMIC) {
     set_error("unknown scatter mode %d", scatter_mode);
     return DPC_ERR_ARG;
   }
-  // clamp(raw,0,1) + raw<=1 mask + blur X + blur Y, in place (identity taps when kernel=None)
+  Workspace w{};
+  if (scatter_mode == DPC_SCATTER_SORTED) {
+    DPC_TRY(check_ws(p, workspace, workspace_bytes));
+    w = carve(p, workspace);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const FwdPtrs q{points, quat, trans, focal, scale, tr_pc, grid_b, clamp_bits, mask, depth, voxels, probs};
+  const int chunk = chunk_size(p);
+  Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
+  if (!pl) return project_fwd_range(p, 0, p->P, q, tx, kx, ty, ky, tz, kz, scatter_mode, w, s);
+  cudaEventRecord(pl->fork, s);
+  for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(pl->side[i], pl->fork, 0);
+  int rc = DPC_OK;
+  for (int b0 = 0, c = 0; b0 < p->P && rc == DPC_OK; b0 += chunk, ++c) {
+    const int n = p->P - b0 < chunk ? p->P - b0 : chunk;
+    rc = project_fwd_range(p, b0, n, q, tx, kx, ty, ky, tz, kz, scatter_mode, w, pl->side[c & 1]);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventRecord(pl->join[i], pl->side[i]);
+    cudaStreamWaitEvent(s, pl->join[i], 0);
+  }
+  return rc;
+}
+
+struct BwdPtrs {
+  const float *points, *quat, *trans, *focal, *scale, *grid_b; const uint32_t *bits;
+  const float *g_mask, *g_depth, *g_probs, *g_voxels, *g_tr_pc;
+  float *g_grid, *g_points;
+};
+
+static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &q, const float *tx,
+                             int kx, const float *ty, int ky, const float *tz, int kz,
+                             const Workspace &w, cudaStream_t s) {
+  dpc_params sp = *p;
+  sp.P = n;
+  const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V, I = (size_t)p->V * p->V;
+  const PoseArgs pa = pose_args(&sp, q.points + b0 * N3, q.quat + b0 * 4,
+                                q.trans ? q.trans + b0 * 3 : nullptr,
+                                q.focal ? q.focal + b0 : nullptr);
+  float *g_grid = q.g_grid + b0 * G;
+  DrcArgs da = drc_args(&sp, q.grid_b + b0 * G, q.scale ? q.scale + b0 : nullptr);
+  da.P_total = p->P;
+  stage_mark(s);
+  DPC_TRY(launch_drc_blurz_bwd(da, tz, kz, q.g_mask ? q.g_mask + b0 * I : nullptr,
+                               q.g_depth ? q.g_depth + b0 * I : nullptr,
+                               q.g_probs ? q.g_probs + b0 * I : nullptr,
+                               q.g_voxels ? q.g_voxels + b0 * G : nullptr, g_grid,
+                               w.scale_partials + (size_t)b0 * drc_scale_partial_blocks(p->V), s));
+  stage_mark(s);
   BlurXYArgs b;
-  b.src = grid_b; b.dst = grid_b; b.bits_out = clamp_bits; b.bits_in = nullptr;
-  b.planes = p->P * p->Vz; b.V = p->V; b.clamp_in = true;
+  b.src = g_grid; b.dst = g_grid; b.bits_out = nullptr; b.bits_in = q.bits + b0 * (G / 32);
+  b.planes = n * p->Vz; b.V = p->V; b.clamp_in = false;
+  // adjoint of a correlation = correlation with the reversed taps
+  float rx[DPC_MAX_TAPS], ry[DPC_MAX_TAPS];
+  for (int i = 0; i < kx; ++i) rx[i] = tx[kx - 1 - i];
+  for (int i = 0; i < ky; ++i) ry[i] = ty[ky - 1 - i];
+  DPC_TRY(launch_blur_xy(b, rx, kx, ry, ky, s));
   stage_mark(s);
-  DPC_TRY(launch_blur_xy(b, tx, kx, ty, ky, s));
-  stage_mark(s);
-  // blur Z + scale + clip + DRC; the blurred occupancy overwrites grid in place (saved for bwd)
-  DPC_TRY(launch_blurz_drc_fwd(drc_args(p, grid_b, scale), tz, kz, grid_b, mask, depth, voxels,
-                               probs, s));
+  DPC_TRY(launch_gather_pose_bwd(pa, g_grid, q.g_tr_pc ? q.g_tr_pc + b0 * N3 : nullptr,
+                                 q.g_points + b0 * N3,
+                                 w.pose_partials + (size_t)b0 * pose_partial_blocks(p->N) * 8, s));
   stage_mark(s);
   return DPC_OK;
 }
@@ -301,22 +429,27 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   DPC_TRY(check_ws(p, workspace, workspace_bytes));
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
+  const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
+                  g_voxels, g_tr_pc, g_grid, g_points};
+  const int chunk = chunk_size(p);
+  Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
+  int rc = DPC_OK;
+  if (!pl) {
+    rc = project_bwd_range(p, 0, p->P, q, tx, kx, ty, ky, tz, kz, w, s);
+  } else {
+    cudaEventRecord(pl->fork, s);
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(pl->side[i], pl->fork, 0);
+    for (int b0 = 0, c = 0; b0 < p->P && rc == DPC_OK; b0 += chunk, ++c) {
+      const int n = p->P - b0 < chunk ? p->P - b0 : chunk;
+      rc = project_bwd_range(p, b0, n, q, tx, kx, ty, ky, tz, kz, w, pl->side[c & 1]);
+    }
+    for (int i = 0; i < 2; ++i) {
+      cudaEventRecord(pl->join[i], pl->side[i]);
+      cudaStreamWaitEvent(s, pl->join[i], 0);
+    }
+  }
+  if (rc != DPC_OK) return rc;
   const PoseArgs pa = pose_args(p, points, quat, trans, focal);
-  stage_mark(s);
-  DPC_TRY(launch_drc_blurz_bwd(drc_args(p, grid_b, scale), tz, kz, g_mask, g_depth, g_probs,
-                               g_voxels, g_grid, w.scale_partials, s));
-  stage_mark(s);
-  BlurXYArgs b;
-  b.src = g_grid; b.dst = g_grid; b.bits_out = nullptr; b.bits_in = clamp_bits;
-  b.planes = p->P * p->Vz; b.V = p->V; b.clamp_in = false;
-  // adjoint of a correlation = correlation with the reversed taps
-  float rx[DPC_MAX_TAPS], ry[DPC_MAX_TAPS];
-  for (int i = 0; i < kx; ++i) rx[i] = tx[kx - 1 - i];
-  for (int i = 0; i < ky; ++i) ry[i] = ty[ky - 1 - i];
-  DPC_TRY(launch_blur_xy(b, rx, kx, ry, ky, s));
-  stage_mark(s);
-  DPC_TRY(launch_gather_pose_bwd(pa, g_grid, g_tr_pc, g_points, w.pose_partials, s));
-  stage_mark(s);
   DPC_TRY(launch_finalize(pa, w.pose_partials, pose_partial_blocks(p->N),
                           scale ? w.scale_partials : nullptr, drc_scale_partial_blocks(p->V),
                           g_quat, trans ? g_trans : nullptr, focal ? g_focal : nullptr,
@@ -342,6 +475,7 @@ int dpc_project_profile(const dpc_params *p, const float *points, const float *q
   for (int it = 0; it < iters && rc == DPC_OK; ++it) {
     tl_stage_events = ev;
     tl_stage_idx = 0;
+    tl_force_single = true;   // whole batch per kernel, on the caller's stream
     rc = dpc_project_fwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, scatter_mode,
                          tr_pc, grid_b, clamp_bits, mask, depth, nullptr, nullptr, workspace,
                          workspace_bytes, stream);
@@ -352,6 +486,7 @@ int dpc_project_profile(const dpc_params *p, const float *points, const float *q
                            g_quat, g_trans, g_focal, g_scale, workspace, workspace_bytes, stream);
     const int nb = tl_stage_idx;  // + 5 events
     tl_stage_events = nullptr;
+    tl_force_single = false;
     if (rc != DPC_OK) break;
     if (cudaStreamSynchronize(s) != cudaSuccess) { rc = check_launch("profile sync"); break; }
     int k = 0;

@@ -91,6 +91,7 @@ struct DrcArgs {
   const float *grid;       // [P,Vz,V,V] input (XY-blurred, or voxels for plain DRC)
   const float *scale;      // [P] or NULL
   int P, Vz, V;
+  int P_total;             // projections in the whole batch (stride of the probs tensor)
   float cam_dist, max_depth, clip;
   int logsum, flip_y;
 };

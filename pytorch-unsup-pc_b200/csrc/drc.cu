@@ -74,13 +74,17 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   return d;
 }
 
-// ring length for a tap radius: 2R+1 taps + a few steps of load-ahead
+// Ring length for a tap radius.  Backward (fed from shared memory): 2R+1 taps
+// + 3.  Forward (fed from global memory): 2R+1 taps + the load-ahead distance
+// that keeps enough bytes in flight per SM to cover DRAM latency.
 template <int R> struct RingLen { static constexpr int L = 2 * R + 1 + 3; };
 template <> struct RingLen<0> { static constexpr int L = 8; };
 template <> struct RingLen<5> { static constexpr int L = 16; };
+template <int R> struct FwdRingLen { static constexpr int L = RingLen<R>::L; };
+template <> struct FwdRingLen<0> { static constexpr int L = 16; };
 
 struct RayConst {
-  int P, Vz;
+  int P, Vz;          // P = projections in the whole batch (probs stride)
   float inv_z, depth0, max_depth, exp_clip;
   float lo_s, hi_s;   // clamp(s*B, 0, 1) bounds; +-inf when there is no scaling factor
   float lo_c, hi_c;   // DRC clip bounds;        +-inf for the product form
@@ -89,7 +93,7 @@ struct RayConst {
 
 static RayConst make_ray_const(const DrcArgs &a) {
   RayConst c;
-  c.P = a.P; c.Vz = a.Vz;
+  c.P = a.P_total; c.Vz = a.Vz;
   c.inv_z = 1.0f / (float)a.Vz;
   c.depth0 = a.cam_dist - 0.5f;
   c.max_depth = a.max_depth;
@@ -139,7 +143,7 @@ __device__ __forceinline__ void pair_index(const RayConst &c, int threads, int &
 template <int V, int R, bool SAVE, typename Sink>
 __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int Vz,
                                                const Taps<R> &taps, Sink &&sink) {
-  constexpr int W = 2 * R + 1, L = RingLen<R>::L, AHEAD = R + (L - W);   // load-ahead in steps
+  constexpr int W = 2 * R + 1, L = FwdRingLen<R>::L, AHEAD = R + (L - W);   // load-ahead in steps
   constexpr int VV = V * V;
   u64 k2[W];
 #pragma unroll
