@@ -64,7 +64,7 @@ def stage_algorithmic_bytes(N, V, Vz):
     G, I = 4 * Vz * V * V, 4 * V * V
     return {"memset": 0, "pose_scatter": G + 36 * N, "blur_xy_fwd": 4 * G,
             "blurz_drc_fwd": G + 2 * I, "drc_blurz_bwd": 2 * G + 2 * I,
-            "blur_xy_bwd": 5 * G, "gather_pose_bwd": G + 36 * N, "finalize": 0}
+            "blur_xy_bwd": 5 * G, "gather_pose_bwd": G + 36 * N}
 
 
 def make_cfg(w):
@@ -398,7 +398,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                 "api": "pytorch_unsup_pc_b200.pointcloud_project_fast + torch.autograd.grad"},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": 6 * args.steps,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src,

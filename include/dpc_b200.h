@@ -155,9 +155,9 @@ DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const floa
  * returns the average duration of each stage in milliseconds.  Synchronises
  * the stream once per iteration -- for profiling only.  Stage order:
  * 0 memset(grid) | 1 pose+scatter | 2 blur XY fwd | 3 blur Z + DRC fwd |
- * 4 DRC bwd + blur Z adjoint | 5 blur XY adjoint | 6 gather + pose adjoint |
- * 7 finalize (quaternion/translation/focal/scale reductions). */
-#define DPC_PROFILE_STAGES 8
+ * 4 DRC bwd + blur Z adjoint | 5 blur XY adjoint |
+ * 6 gather + pose adjoint + fused quaternion/translation/focal/scale reduction. */
+#define DPC_PROFILE_STAGES 7
 DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,
                     const float *trans, const float *focal, const float *scale,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,

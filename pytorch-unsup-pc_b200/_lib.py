@@ -59,7 +59,7 @@ SIGNATURES = {
                            + [c_void_p, c_size_t, c_void_p, c_int, c_void_p],
 }
 PROFILE_STAGES = ("memset", "pose_scatter", "blur_xy_fwd", "blurz_drc_fwd", "drc_blurz_bwd",
-                  "blur_xy_bwd", "gather_pose_bwd", "finalize")
+                  "blur_xy_bwd", "gather_pose_bwd")
 _RESTYPES = {"dpc_last_error": ctypes.c_char_p, "dpc_workspace_bytes": c_size_t}
 
 _lib = None

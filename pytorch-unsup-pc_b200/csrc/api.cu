@@ -40,6 +40,7 @@ static inline void stage_mark(cudaStream_t s) {
 struct Workspace {
   double *pose_partials;
   float *scale_partials;
+  int *counters;          // P ints: per-projection arrival counters of the fused finalize
   void *sorted;
   size_t sorted_bytes;
   size_t total;
@@ -53,6 +54,8 @@ static Workspace carve(const dpc_params *p, void *base) {
   off += align256((size_t)p->P * pose_partial_blocks(p->N) * 8 * sizeof(double));
   w.scale_partials = (float *)(c + off);
   off += align256((size_t)p->P * drc_scale_partial_blocks(p->V) * sizeof(float));
+  w.counters = (int *)(c + off);
+  off += align256((size_t)p->P * sizeof(int));
   w.sorted = (void *)(c + off);
   w.sorted_bytes = sorted_workspace_bytes(p->P, p->N, p->Vz, p->V);
   off += align256(w.sorted_bytes);
@@ -226,7 +229,7 @@ int dpc_drc_bwd(const dpc_params *p, const float *voxels, const float *g_mask, c
   DPC_TRY(check_params(p, false));
   DPC_REQUIRE(voxels); DPC_REQUIRE(g_voxels);
   return launch_drc_blurz_bwd(drc_args(p, voxels, nullptr), nullptr, 0, g_mask, g_depth, g_probs,
-                              nullptr, g_voxels, nullptr, (cudaStream_t)stream);
+                              nullptr, g_voxels, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int dpc_depth_from_probs_fwd(const dpc_params *p, const float *probs, float *depth, void *stream) {
@@ -376,7 +379,7 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
 struct BwdPtrs {
   const float *points, *quat, *trans, *focal, *scale, *grid_b; const uint32_t *bits;
   const float *g_mask, *g_depth, *g_probs, *g_voxels, *g_tr_pc;
-  float *g_grid, *g_points;
+  float *g_grid, *g_points, *g_quat, *g_trans, *g_focal, *g_scale;
 };
 
 static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &q, const float *tx,
@@ -396,7 +399,8 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
                                q.g_depth ? q.g_depth + b0 * I : nullptr,
                                q.g_probs ? q.g_probs + b0 * I : nullptr,
                                q.g_voxels ? q.g_voxels + b0 * G : nullptr, g_grid,
-                               w.scale_partials + (size_t)b0 * drc_scale_partial_blocks(p->V), s));
+                               w.scale_partials + (size_t)b0 * drc_scale_partial_blocks(p->V),
+                               w.counters + b0, n, s));
   stage_mark(s);
   BlurXYArgs b;
   b.src = g_grid; b.dst = g_grid; b.bits_out = nullptr; b.bits_in = q.bits + b0 * (G / 32);
@@ -407,9 +411,15 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
   for (int i = 0; i < ky; ++i) ry[i] = ty[ky - 1 - i];
   DPC_TRY(launch_blur_xy(b, rx, kx, ry, ky, s));
   stage_mark(s);
-  DPC_TRY(launch_gather_pose_bwd(pa, g_grid, q.g_tr_pc ? q.g_tr_pc + b0 * N3 : nullptr,
-                                 q.g_points + b0 * N3,
-                                 w.pose_partials + (size_t)b0 * pose_partial_blocks(p->N) * 8, s));
+  // gather + pose adjoint; the last block of each projection also reduces the partials
+  DPC_TRY(launch_gather_pose_finalize(
+      pa, g_grid, q.g_tr_pc ? q.g_tr_pc + b0 * N3 : nullptr, q.g_points + b0 * N3,
+      w.pose_partials + (size_t)b0 * pose_partial_blocks(p->N) * 8, w.counters + b0,
+      q.scale ? w.scale_partials + (size_t)b0 * drc_scale_partial_blocks(p->V) : nullptr,
+      drc_scale_partial_blocks(p->V), q.g_quat ? q.g_quat + b0 * 4 : nullptr,
+      (q.trans && q.g_trans) ? q.g_trans + b0 * 3 : nullptr,
+      (q.focal && q.g_focal) ? q.g_focal + b0 : nullptr,
+      (q.scale && q.g_scale) ? q.g_scale + b0 : nullptr, s));
   stage_mark(s);
   return DPC_OK;
 }
@@ -430,7 +440,7 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
-                  g_voxels, g_tr_pc, g_grid, g_points};
+                  g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale};
   const int chunk = chunk_size(p);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   int rc = DPC_OK;
@@ -448,14 +458,7 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
       cudaStreamWaitEvent(s, pl->join[i], 0);
     }
   }
-  if (rc != DPC_OK) return rc;
-  const PoseArgs pa = pose_args(p, points, quat, trans, focal);
-  DPC_TRY(launch_finalize(pa, w.pose_partials, pose_partial_blocks(p->N),
-                          scale ? w.scale_partials : nullptr, drc_scale_partial_blocks(p->V),
-                          g_quat, trans ? g_trans : nullptr, focal ? g_focal : nullptr,
-                          scale ? g_scale : nullptr, s));
-  stage_mark(s);
-  return DPC_OK;
+  return rc;
 }
 
 int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,

@@ -58,10 +58,15 @@ struct XYCfg {
   static constexpr int YTASKS = (V / 2) * (V / J);
   static constexpr int THREADS = YTASKS < 128 ? YTASKS : (V == 128 ? 256 : 128);
   static constexpr int FILL_ITEMS = (RH / 2) * (V / 4);
-  static constexpr size_t SMEM = (size_t)(RH / 2 + V / 2) * S * sizeof(float2);
+  // V <= 64: the X-pass results wait in registers while the tile is reused for
+  // the transposed layout, so one tile suffices (22 KB -> 9-10 CTAs per SM)
+  static constexpr bool ONE_TILE = (RH == V);
+  static constexpr int TILE_LINES = ONE_TILE ? V / 2 : RH / 2 + V / 2;
+  static constexpr size_t SMEM = (size_t)TILE_LINES * S * sizeof(float2);
+  static constexpr int MINB = V == 64 ? 9 : 1;
   static_assert(V % 32 == 0, "V must be a multiple of 32");
-  static_assert(R % 2 == 0 || true, "");
   static_assert(FILL_ITEMS % THREADS == 0, "fill loop must be warp-uniform");
+  static_assert(!ONE_TILE || XTASKS == THREADS, "one-tile mode: one X task per thread");
 };
 
 // 16 packed outputs from a window of W pair-positions starting at `win`
@@ -99,7 +104,7 @@ __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
 }
 
 template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT>
-__global__ void __launch_bounds__(XYCfg<V, R>::THREADS)
+__global__ void __launch_bounds__(XYCfg<V, R>::THREADS, XYCfg<V, R>::MINB)
 blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                uint32_t *__restrict__ bits_out, const uint32_t *__restrict__ bits_in,
                const Taps<R> kx, const Taps<R> ky) {
@@ -107,13 +112,13 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   constexpr int HALF = C::RH / 2;
   extern __shared__ __align__(16) float2 smem2[];
   float2 *A2 = smem2;                  // [RH/2][S]  (row r, row r + RH/2), x padded by R
-  float2 *B2 = smem2 + HALF * C::S;    // [V/2][S]   (col 2c, col 2c+1),    y padded by R
+  float2 *B2 = C::ONE_TILE ? smem2 : smem2 + HALF * C::S;   // [V/2][S] (col 2c, col 2c+1), y padded
   const int tid = threadIdx.x;
   const size_t plane = blockIdx.x;
   const float *sp = src + plane * V * V;
 
   // zero both tiles once (the pads stay zero for the whole kernel)
-  for (int i = tid; i < (HALF + V / 2) * C::S / 2; i += C::THREADS)
+  for (int i = tid; i < C::TILE_LINES * C::S / 2; i += C::THREADS)
     reinterpret_cast<float4 *>(smem2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   u64 k2[2 * R + 1];
 #pragma unroll
@@ -161,6 +166,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       const int rp = task % HALF, x0 = (task / HALF) * C::J;
       u64 acc[C::J];
       window_fma2<R, C::J, C::W2>(A2 + rp * C::S + x0, k2, acc);
+      if (C::ONE_TILE) __syncthreads();   // every window is in registers: the tile can be reused
       // acc[j] = (out[r0][x0+j], out[r1][x0+j]) -> B2[(x0+j)/2][R + row] = (even col, odd col)
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;
       float2 *b = B2 + (x0 / 2) * C::S + R;

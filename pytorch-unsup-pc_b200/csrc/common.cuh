@@ -70,6 +70,11 @@ int launch_gather_pose_bwd(const PoseArgs &a, const float *g_grid, const float *
                            float *g_points, double *partials, cudaStream_t s);
 int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, const float *g_grid,
                            float *g_trpc, cudaStream_t s);
+// gather + pose adjoint + fused last-block finalize (counters: P ints, zeroed beforehand)
+int launch_gather_pose_finalize(const PoseArgs &a, const float *g_grid, const float *g_trpc,
+                                float *g_points, double *partials, int *counters,
+                                const float *scale_partials, int scale_blocks, float *g_quat,
+                                float *g_trans, float *g_focal, float *g_scale, cudaStream_t s);
 int pose_partial_blocks(int N);
 // reduce the per-block partials: g_quat/g_trans/g_focal/g_scale (each NULL ok)
 int launch_finalize(const PoseArgs &a, const double *pose_partials, int pose_blocks,
@@ -100,9 +105,11 @@ int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave
                          float *depth, float *voxels, float *probs, cudaStream_t s);
 int drc_scale_partial_blocks(int V);
 // a.grid = blurZ-ed grid saved by the forward (or the plain voxels when kz == 0)
+// zero_ints/n_zero (NULL ok): block 0 clears this int array (the finalize counters)
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
-                         float *g_grid, float *scale_partials, cudaStream_t s);
+                         float *g_grid, float *scale_partials, int *zero_ints, int n_zero,
+                         cudaStream_t s);
 int launch_blur_z(const float *src, float *dst, int P, int Vz, int V, const float *tz, int kz,
                   cudaStream_t s);
 int launch_depth_from_probs(const float *probs, float *depth, int P, int Vz, int V,

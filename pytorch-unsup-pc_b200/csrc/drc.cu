@@ -227,8 +227,10 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
                      const Taps<R> kz, const float *__restrict__ g_mask,
                      const float *__restrict__ g_depth, const float *__restrict__ g_probs,
                      const float *__restrict__ g_voxels, float *__restrict__ g_grid,
-                     float *__restrict__ scale_partials) {
+                     float *__restrict__ scale_partials, int *__restrict__ zero_ints, int n_zero) {
   constexpr int W = 2 * R + 1, L = RingLen<R>::L;   // block length == ring length
+  if (zero_ints && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kBwdThreads) zero_ints[i] = 0;
   constexpr int VV = V * V;
   extern __shared__ float2 sm2[];
   float2 *sB = sm2 + threadIdx.x;                        // [Vz][threads]    saved blurZ pair
@@ -462,7 +464,7 @@ template <int V, int R, bool EXTRA>
 static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
                            const float *g_mask, const float *g_depth, const float *g_probs,
                            const float *g_voxels, float *g_grid, float *scale_partials,
-                           cudaStream_t s) {
+                           int *zero_ints, int n_zero, cudaStream_t s) {
   constexpr int L = RingLen<R>::L;
   const int nblk = (a.Vz + L - 1) / L;
   const size_t smem = (size_t)(a.Vz + nblk) * kBwdThreads * sizeof(float2);
@@ -475,22 +477,24 @@ static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &t
   const int blocks = a.P * (V * V / 2) / kBwdThreads;
   drc_blurz_bwd_kernel<V, R, EXTRA><<<blocks, kBwdThreads, smem, s>>>(
       a.grid, a.scale, c, taps, g_mask, g_depth, g_probs, g_voxels, g_grid,
-      a.scale ? scale_partials : nullptr);
+      a.scale ? scale_partials : nullptr, zero_ints, n_zero);
 }
 
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
-                         float *g_grid, float *scale_partials, cudaStream_t s) {
+                         float *g_grid, float *scale_partials, int *zero_ints, int n_zero,
+                         cudaStream_t s) {
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
   if (g_probs || g_voxels) {
     DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_one<V, R, true>(
                                               a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, g_probs,
-                                              g_voxels, g_grid, scale_partials, s)));
+                                              g_voxels, g_grid, scale_partials, zero_ints, n_zero, s)));
   } else {
     DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_one<V, R, false>(
                                               a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, nullptr,
-                                              nullptr, g_grid, scale_partials, s)));
+                                              nullptr, g_grid, scale_partials, zero_ints,
+                                              n_zero, s)));
   }
   return check_launch("drc_blurz_bwd");
 }

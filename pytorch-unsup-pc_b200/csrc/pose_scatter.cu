@@ -139,11 +139,69 @@ gather_trpc_bwd_kernel(const float *__restrict__ tr_pc, int N, int Vz, int V,
   g_trpc[pi + 2] = (float)gx;
 }
 
+// Final reduction for one projection by one warp: lanes stride over the
+// per-block partials, a fixed shuffle tree combines them (same order every
+// run), and lane 0 applies the quaternion-normalisation Jacobian
+//   dL/dq = (dL/dq^ - q^ (q^ . dL/dq^)) / |q|         (quaternion.py:119-121)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct FinalizeArgs {
+  const double *pose_partials;   // [P][pose_blocks][8] or NULL
+  const float *scale_partials;   // [P][scale_blocks]   or NULL
+  int pose_blocks, scale_blocks;
+  float *g_quat, *g_trans, *g_focal, *g_scale;
+};
+
+__device__ __forceinline__ void finalize_projection(const PoseArgs &a, const FinalizeArgs &f,
+                                                    int b, int lane) {
+  if (f.pose_partials) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < f.pose_blocks; k += 32) {
+      const double *p = f.pose_partials + ((size_t)b * f.pose_blocks + k) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += __ldcg(p + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+      if (f.g_quat) {
+        const Quat q = load_quat(a.quat + 4 * b);
+        const double dot = q.w * acc[0] + q.x * acc[1] + q.y * acc[2] + q.z * acc[3];
+        f.g_quat[4 * b] = (float)((acc[0] - q.w * dot) * q.inv_norm);
+        f.g_quat[4 * b + 1] = (float)((acc[1] - q.x * dot) * q.inv_norm);
+        f.g_quat[4 * b + 2] = (float)((acc[2] - q.y * dot) * q.inv_norm);
+        f.g_quat[4 * b + 3] = (float)((acc[3] - q.z * dot) * q.inv_norm);
+      }
+      if (f.g_trans) {
+        f.g_trans[3 * b] = (float)acc[4];
+        f.g_trans[3 * b + 1] = (float)acc[5];
+        f.g_trans[3 * b + 2] = (float)acc[6];
+      }
+      if (f.g_focal) f.g_focal[b] = (float)acc[7];
+    }
+  }
+  if (f.scale_partials && f.g_scale) {
+    double v = 0;
+    for (int k = lane; k < f.scale_blocks; k += 32)
+      v += (double)__ldcg(f.scale_partials + (size_t)b * f.scale_blocks + k);
+    v = warp_sum(v);
+    if (lane == 0) f.g_scale[b] = (float)v;
+  }
+}
+
+__global__ void finalize_kernel(PoseArgs a, FinalizeArgs f) {
+  finalize_projection(a, f, blockIdx.x, threadIdx.x);
+}
+
 // partials[b][block][8] = {dq^_w, dq^_x, dq^_y, dq^_z, dt0, dt1, dt2, df}
 __global__ void __launch_bounds__(kPoseThreads)
 gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
                        const float *__restrict__ g_trpc, float *__restrict__ g_points,
-                       double *__restrict__ partials) {
+                       double *__restrict__ partials, int *__restrict__ counters, FinalizeArgs fin) {
   const int b = blockIdx.y;
   const int n = blockIdx.x * kPoseThreads + threadIdx.x;
   const Quat q = load_quat(a.quat + 4 * b);
@@ -215,56 +273,20 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     for (int wdx = 0; wdx < kPoseThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
     partials[((size_t)b * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
   }
-}
-
-// One warp per projection: lanes stride over the per-block partials, then a
-// fixed shuffle tree combines them (same order every run), and lane 0 applies
-// the quaternion-normalisation Jacobian
-//   dL/dq = (dL/dq^ - q^ (q^ . dL/dq^)) / |q|         (quaternion.py:119-121)
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__global__ void finalize_kernel(PoseArgs a, const double *__restrict__ pose_partials,
-                                int pose_blocks, const float *__restrict__ scale_partials,
-                                int scale_blocks, float *__restrict__ g_quat,
-                                float *__restrict__ g_trans, float *__restrict__ g_focal,
-                                float *__restrict__ g_scale) {
-  const int b = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (pose_partials) {
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = lane; k < pose_blocks; k += 32) {
-      const double *p = pose_partials + ((size_t)b * pose_blocks + k) * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += p[i];
+  // Fused finalize: the last block of a projection to arrive reduces all of the
+  // projection's partials (in block-index order, so the result does not depend
+  // on which block happens to be last).  counters[] is zeroed by the DRC
+  // backward kernel earlier in the same pass.
+  if (counters) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counters + b, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+      __threadfence();
+      finalize_projection(a, fin, b, threadIdx.x);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
-      if (g_quat) {
-        const Quat q = load_quat(a.quat + 4 * b);
-        const double dot = q.w * acc[0] + q.x * acc[1] + q.y * acc[2] + q.z * acc[3];
-        g_quat[4 * b] = (float)((acc[0] - q.w * dot) * q.inv_norm);
-        g_quat[4 * b + 1] = (float)((acc[1] - q.x * dot) * q.inv_norm);
-        g_quat[4 * b + 2] = (float)((acc[2] - q.y * dot) * q.inv_norm);
-        g_quat[4 * b + 3] = (float)((acc[3] - q.z * dot) * q.inv_norm);
-      }
-      if (g_trans) {
-        g_trans[3 * b] = (float)acc[4];
-        g_trans[3 * b + 1] = (float)acc[5];
-        g_trans[3 * b + 2] = (float)acc[6];
-      }
-      if (g_focal) g_focal[b] = (float)acc[7];
-    }
-  }
-  if (scale_partials && g_scale) {
-    double v = 0;
-    for (int k = lane; k < scale_blocks; k += 32) v += (double)scale_partials[(size_t)b * scale_blocks + k];
-    v = warp_sum(v);
-    if (lane == 0) g_scale[b] = (float)v;
   }
 }
 
@@ -290,8 +312,20 @@ int launch_scatter_trpc(const float *tr_pc, int P, int N, int Vz, int V, float *
 int launch_gather_pose_bwd(const PoseArgs &a, const float *g_grid, const float *g_trpc,
                            float *g_points, double *partials, cudaStream_t s) {
   dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
-  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials);
+  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, nullptr,
+                                         FinalizeArgs{});
   return check_launch("gather_pose_bwd");
+}
+
+int launch_gather_pose_finalize(const PoseArgs &a, const float *g_grid, const float *g_trpc,
+                                float *g_points, double *partials, int *counters,
+                                const float *scale_partials, int scale_blocks, float *g_quat,
+                                float *g_trans, float *g_focal, float *g_scale, cudaStream_t s) {
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
+                 g_quat, g_trans, g_focal, g_scale};
+  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, counters, f);
+  return check_launch("gather_pose_finalize");
 }
 
 int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, const float *g_grid,
@@ -304,8 +338,9 @@ int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, cons
 int launch_finalize(const PoseArgs &a, const double *pose_partials, int pose_blocks,
                     const float *scale_partials, int scale_blocks, float *g_quat, float *g_trans,
                     float *g_focal, float *g_scale, cudaStream_t s) {
-  finalize_kernel<<<a.P, 32, 0, s>>>(a, pose_partials, pose_blocks, scale_partials, scale_blocks,
-                                     g_quat, g_trans, g_focal, g_scale);
+  FinalizeArgs f{pose_partials, scale_partials, pose_blocks, scale_blocks,
+                 g_quat, g_trans, g_focal, g_scale};
+  finalize_kernel<<<a.P, 32, 0, s>>>(a, f);
   return check_launch("finalize");
 }
 

@@ -97,7 +97,7 @@ class ProjectFn(torch.autograd.Function):
 
     forward : memset + pose/scatter + blur XY (in place) + blur Z/DRC  (4 launches)
     backward: DRC reverse scan/blur Z adjoint + blur XY adjoint + gather/pose
-              adjoint + finalize                                       (4 launches)
+              adjoint with fused final reductions                      (3 launches)
     Saved for backward: the inputs, the blurred grid and a 1-bit clamp mask.
     """
 
