@@ -235,7 +235,9 @@ def run_b200(args, rank, world, local_rank):
                bits=torch.empty(P, Vz, V, V // 32, dtype=torch.int32, device=dev),
                mask=torch.empty(P, V, V, **f32), depth=torch.empty(P, V, V, **f32),
                g_grid=torch.empty(P, Vz, V, V, **f32), g_points=torch.empty(P, N, 3, **f32),
-               g_quat=torch.empty(P, 4, **f32), g_scale=torch.empty(P, **f32))
+               g_quat=torch.empty(P, 4, **f32), g_scale=torch.empty(P, **f32),
+               cells=torch.empty(lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8,
+                                 device=dev))
     ws = torch.empty(lib.dpc_workspace_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sptr = ctypes.c_void_p(stream.cuda_stream)
@@ -246,12 +248,12 @@ def run_b200(args, rank, world, local_rank):
         d = devin[i % N_INPUT_SETS]
         st = lib.dpc_project_fwd(ctypes.byref(params), P_(d["points"]), P_(d["quat"]), None, None,
                                  P_(d["scale"]), *tap_args, _lib.SCATTER_ATOMIC, P_(buf["tr_pc"]),
-                                 P_(buf["grid"]), P_(buf["bits"]), P_(buf["mask"]),
+                                 P_(buf["grid"]), P_(buf["bits"]), P_(buf["cells"]), P_(buf["mask"]),
                                  P_(buf["depth"]), None, None, P_(ws), ws.numel(), sptr)
         _lib.check(st, "project_fwd")
         st = lib.dpc_project_bwd(ctypes.byref(params), P_(d["points"]), P_(d["quat"]), None, None,
                                  P_(d["scale"]), *tap_args, P_(buf["grid"]), P_(buf["bits"]),
-                                 P_(d["g_mask"]), P_(d["g_depth"]), None, None, None,
+                                 P_(buf["cells"]), P_(d["g_mask"]), P_(d["g_depth"]), None, None, None,
                                  P_(buf["g_grid"]), P_(buf["g_points"]), P_(buf["g_quat"]), None,
                                  None, P_(buf["g_scale"]), P_(ws), ws.numel(), sptr)
         _lib.check(st, "project_bwd")
@@ -350,8 +352,8 @@ def run_b200(args, rank, world, local_rank):
     d = devin[0]
     st = lib.dpc_project_profile(
         ctypes.byref(params), P_(d["points"]), P_(d["quat"]), None, None, P_(d["scale"]), *tap_args,
-        _lib.SCATTER_ATOMIC, P_(buf["tr_pc"]), P_(buf["grid"]), P_(buf["bits"]), P_(buf["mask"]),
-        P_(buf["depth"]), P_(d["g_mask"]), P_(d["g_depth"]), P_(buf["g_grid"]), P_(buf["g_points"]),
+        _lib.SCATTER_ATOMIC, P_(buf["tr_pc"]), P_(buf["grid"]), P_(buf["bits"]), P_(buf["cells"]),
+        P_(buf["mask"]), P_(buf["depth"]), P_(d["g_mask"]), P_(d["g_depth"]), P_(buf["g_grid"]), P_(buf["g_points"]),
         P_(buf["g_quat"]), None, None, P_(buf["g_scale"]), P_(ws), ws.numel(), sptr,
         min(max(args.steps, 10), 50), stage_ms)
     _lib.check(st, "project_profile")

@@ -42,7 +42,7 @@ extern "C" {
 #define DPC_API
 #endif
 
-#define DPC_B200_VERSION 100
+#define DPC_B200_VERSION 110
 #define DPC_MAX_TAPS 21
 
 typedef enum {
@@ -74,6 +74,10 @@ DPC_API const char *dpc_last_error(void);
 /* Bytes of workspace the calls below need for this geometry (one buffer is
  * shared by all of them; 256-byte aligned). */
 DPC_API size_t dpc_workspace_bytes(const dpc_params *p);
+
+/* Bytes of the per-point cell records dpc_project_fwd saves for dpc_project_bwd
+ * (z cell byte + {iy,ix,rz,ry,rx} per point; about 17 bytes per point). */
+DPC_API size_t dpc_cells_bytes(const dpc_params *p);
 
 /* ---- a1+a2: quaternion.py:110-132 quaternion_rotate +
  *      point_cloud_to.py:118-178 pc_perspective_transform ------------------ */
@@ -120,15 +124,21 @@ DPC_API int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, 
  * The whole path in one call: pose -> scatter -> clamp -> blur XY (in place)
  * -> blur Z (in place) + scale + clip + DRC ray march (+ Y flips).
  * Saved for backward: grid_b [P,Vz,V,V] (the blurred occupancy B, before
- * scaling) and clamp_bits (raw <= 1 mask).  voxels/probs are written only
- * when non-NULL.
+ * scaling), clamp_bits (raw <= 1 mask) and cells (dpc_cells_bytes; NULL ok).
+ * With cells != NULL and DPC_SCATTER_ATOMIC the plane-local path runs: the raw
+ * grid never exists in global memory -- a pose kernel writes the cell records
+ * and every Z-plane is built in shared memory by the blur kernel from the
+ * points that touch it (forward), and gathered from shared memory (backward).
+ * With cells == NULL (or DPC_SCATTER_SORTED) the grid is scattered in global
+ * memory first.  Pass the same cells pointer (or NULL) to dpc_project_bwd.
+ * voxels/probs are written only when non-NULL.
  * ntaps == 0 means kernel=None (no blur). */
 DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
                     const float *trans /*NULL ok*/, const float *focal /*NULL ok*/,
                     const float *scale /*NULL ok*/,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,
                     const float *taps_z_host, int kz, int scatter_mode,
-                    float *tr_pc, float *grid_b, uint32_t *clamp_bits,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells /*NULL ok*/,
                     float *mask, float *depth,
                     float *voxels /*NULL ok*/, float *probs /*NULL ok*/,
                     void *workspace, size_t workspace_bytes, void *stream);
@@ -142,7 +152,7 @@ DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const floa
                     const float *trans, const float *focal, const float *scale,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,
                     const float *taps_z_host, int kz,
-                    const float *grid_b, const uint32_t *clamp_bits,
+                    const float *grid_b, const uint32_t *clamp_bits, const void *cells /*NULL ok*/,
                     const float *g_mask /*NULL ok*/, const float *g_depth /*NULL ok*/,
                     const float *g_probs /*NULL ok*/, const float *g_voxels /*NULL ok*/,
                     const float *g_tr_pc /*NULL ok*/,
@@ -154,16 +164,18 @@ DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const floa
  * `iters` times with a CUDA event recorded on `stream` after every stage and
  * returns the average duration of each stage in milliseconds.  Synchronises
  * the stream once per iteration -- for profiling only.  Stage order:
- * 0 memset(grid) | 1 pose+scatter | 2 blur XY fwd | 3 blur Z + DRC fwd |
- * 4 DRC bwd + blur Z adjoint | 5 blur XY adjoint |
- * 6 gather + pose adjoint + fused quaternion/translation/focal/scale reduction. */
+ * 0 memset(grid) (nothing on the plane-local path) | 1 pose + scatter (pose +
+ * cell records on the plane-local path) | 2 [plane scatter +] blur XY fwd |
+ * 3 blur Z + DRC fwd | 4 DRC bwd + blur Z adjoint | 5 blur XY adjoint [+ plane
+ * gather] | 6 [gather +] pose adjoint + fused quaternion/translation/focal/scale
+ * reduction. */
 #define DPC_PROFILE_STAGES 7
 DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,
                     const float *trans, const float *focal, const float *scale,
                     const float *taps_x_host, int kx, const float *taps_y_host, int ky,
                     const float *taps_z_host, int kz, int scatter_mode,
-                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, float *mask, float *depth,
-                    const float *g_mask, const float *g_depth,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells /*NULL ok*/,
+                    float *mask, float *depth, const float *g_mask, const float *g_depth,
                     float *g_grid, float *g_points, float *g_quat, float *g_trans,
                     float *g_focal, float *g_scale,
                     void *workspace, size_t workspace_bytes, void *stream,

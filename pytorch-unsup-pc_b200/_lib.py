@@ -36,6 +36,7 @@ SIGNATURES = {
     "dpc_version": [],
     "dpc_last_error": [],
     "dpc_workspace_bytes": [_P],
+    "dpc_cells_bytes": [_P],
     "dpc_pose_fwd": [_P] + [c_void_p] * 5 + [c_void_p],
     "dpc_pose_bwd": [_P] + [c_void_p] * 9 + [c_void_p, c_size_t, c_void_p],
     "dpc_scatter_fwd": [_P, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
@@ -48,19 +49,20 @@ SIGNATURES = {
     "dpc_depth_from_probs_bwd": [_P, c_void_p, c_void_p, c_void_p],
     "dpc_project_fwd": [_P] + [c_void_p] * 5
                        + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
-                       + [c_void_p] * 7 + [c_void_p, c_size_t, c_void_p],
+                       + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p],
     "dpc_project_bwd": [_P] + [c_void_p] * 5
                        + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
-                       + [c_void_p] * 2 + [c_void_p] * 5 + [c_void_p] * 6
+                       + [c_void_p] * 3 + [c_void_p] * 5 + [c_void_p] * 6
                        + [c_void_p, c_size_t, c_void_p],
     "dpc_project_profile": [_P] + [c_void_p] * 5
                            + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
-                           + [c_void_p] * 5 + [c_void_p] * 2 + [c_void_p] * 6
+                           + [c_void_p] * 6 + [c_void_p] * 2 + [c_void_p] * 6
                            + [c_void_p, c_size_t, c_void_p, c_int, c_void_p],
 }
 PROFILE_STAGES = ("memset", "pose_scatter", "blur_xy_fwd", "blurz_drc_fwd", "drc_blurz_bwd",
                   "blur_xy_bwd", "gather_pose_bwd")
-_RESTYPES = {"dpc_last_error": ctypes.c_char_p, "dpc_workspace_bytes": c_size_t}
+_RESTYPES = {"dpc_last_error": ctypes.c_char_p, "dpc_workspace_bytes": c_size_t,
+             "dpc_cells_bytes": c_size_t}
 
 _lib = None
 

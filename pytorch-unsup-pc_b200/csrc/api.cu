@@ -43,6 +43,7 @@ struct Workspace {
   int *counters;          // P ints: per-projection arrival counters of the fused finalize
   void *sorted;
   size_t sorted_bytes;
+  float4 *part;           // [2][P][N] per-plane partial gathers of the backward (plane-local path)
   size_t total;
 };
 
@@ -59,6 +60,8 @@ static Workspace carve(const dpc_params *p, void *base) {
   w.sorted = (void *)(c + off);
   w.sorted_bytes = sorted_workspace_bytes(p->P, p->N, p->Vz, p->V);
   off += align256(w.sorted_bytes);
+  w.part = (float4 *)(c + off);
+  off += align256((size_t)2 * p->P * p->N * sizeof(float4));
   w.total = off;
   return w;
 }
@@ -146,6 +149,11 @@ using namespace dpc;
 extern "C" {
 
 int dpc_version(void) { return DPC_B200_VERSION; }
+
+size_t dpc_cells_bytes(const dpc_params *p) {
+  if (!p || p->P < 1 || p->N < 1) return 0;
+  return cells_bytes(p->P, p->N, p->Vz);
+}
 const char *dpc_last_error(void) { return g_err; }
 
 size_t dpc_workspace_bytes(const dpc_params *p) {
@@ -294,7 +302,18 @@ static int chunk_size(const dpc_params *p) {
 struct FwdPtrs {
   const float *points, *quat, *trans, *focal, *scale;
   float *tr_pc, *grid_b; uint32_t *bits; float *mask, *depth, *voxels, *probs;
+  void *cells;
 };
+
+// the records of projections [b0, b0 + n) inside a whole-batch cells buffer
+static CellsView cells_range(void *base, const dpc_params *p, int b0) {
+  CellsView v = cells_view(base, p->P, p->N, p->Vz);
+  v.cellz += (size_t)b0 * v.Npad;
+  v.rec += (size_t)b0 * p->N;
+  v.order += (size_t)b0 * p->N;
+  v.binstart += (size_t)b0 * v.zstride;
+  return v;
+}
 
 // projections [b0, b0+n) of the forward pass on stream s
 static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &q, const float *tx,
@@ -309,7 +328,18 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   float *grid = q.grid_b + b0 * G;
   float *tr_pc = q.tr_pc ? q.tr_pc + b0 * N3 : nullptr;
   stage_mark(s);
-  if (scatter_mode == DPC_SCATTER_SORTED) {
+  // clamp(raw,0,1) + raw<=1 mask + blur X + blur Y, in place (identity taps when kernel=None)
+  BlurXYArgs b;
+  b.src = grid; b.dst = grid; b.bits_out = q.bits + b0 * (G / 32); b.bits_in = nullptr;
+  b.planes = n * p->Vz; b.V = p->V; b.clamp_in = true;
+  if (q.cells && scatter_mode == DPC_SCATTER_ATOMIC) {
+    // plane-local path: pose -> cell records; every Z-plane is then built in
+    // shared memory by the blur kernel itself (no memset, no global atomics)
+    stage_mark(s);
+    b.cells = cells_range(q.cells, p, b0);
+    b.Vz = p->Vz; b.N = p->N; b.P = n;
+    DPC_TRY(launch_pose_cells(pa, tr_pc, b.cells, s));
+  } else if (scatter_mode == DPC_SCATTER_SORTED) {
     stage_mark(s);
     DPC_TRY(launch_scatter_sorted(&pa, nullptr, n, p->N, p->Vz, p->V, tr_pc, grid,
                                   (uint32_t *)w.sorted + (size_t)2 * b0 * p->N,
@@ -320,10 +350,6 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
     stage_mark(s);
     DPC_TRY(launch_pose_scatter(pa, tr_pc, grid, s));
   }
-  // clamp(raw,0,1) + raw<=1 mask + blur X + blur Y, in place (identity taps when kernel=None)
-  BlurXYArgs b;
-  b.src = grid; b.dst = grid; b.bits_out = q.bits + b0 * (G / 32); b.bits_in = nullptr;
-  b.planes = n * p->Vz; b.V = p->V; b.clamp_in = true;
   stage_mark(s);
   DPC_TRY(launch_blur_xy(b, tx, kx, ty, ky, s));
   stage_mark(s);
@@ -340,12 +366,13 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
 int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
                     const float *ty, int ky, const float *tz, int kz, int scatter_mode,
-                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, float *mask, float *depth,
-                    float *voxels, float *probs, void *workspace, size_t workspace_bytes,
-                    void *stream) {
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells, float *mask,
+                    float *depth, float *voxels, float *probs, void *workspace,
+                    size_t workspace_bytes, void *stream) {
   DPC_TRY(check_params(p, true));
   DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
   DPC_REQUIRE(mask);
+  if (scatter_mode == DPC_SCATTER_SORTED) cells = nullptr;   // the sorted scatter builds the grid itself
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
   DPC_TRY(check_taps(tz, kz, "taps_z"));
   if (scatter_mode != DPC_SCATTER_SORTED && scatter_mode != DPC_SCATTER_ATOMIC) {
@@ -358,7 +385,8 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
     w = carve(p, workspace);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const FwdPtrs q{points, quat, trans, focal, scale, tr_pc, grid_b, clamp_bits, mask, depth, voxels, probs};
+  const FwdPtrs q{points, quat, trans, focal, scale, tr_pc, grid_b, clamp_bits, mask, depth, voxels,
+                  probs, cells};
   const int chunk = chunk_size(p);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   if (!pl) return project_fwd_range(p, 0, p->P, q, tx, kx, ty, ky, tz, kz, scatter_mode, w, s);
@@ -380,6 +408,7 @@ struct BwdPtrs {
   const float *points, *quat, *trans, *focal, *scale, *grid_b; const uint32_t *bits;
   const float *g_mask, *g_depth, *g_probs, *g_voxels, *g_tr_pc;
   float *g_grid, *g_points, *g_quat, *g_trans, *g_focal, *g_scale;
+  void *cells;
 };
 
 static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &q, const float *tx,
@@ -409,8 +438,28 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
   float rx[DPC_MAX_TAPS], ry[DPC_MAX_TAPS];
   for (int i = 0; i < kx; ++i) rx[i] = tx[kx - 1 - i];
   for (int i = 0; i < ky; ++i) ry[i] = ty[ky - 1 - i];
+  float4 *part = nullptr;
+  if (q.cells) {
+    // plane-local path: the masked dL/draw plane is gathered at the touching
+    // points' corners straight from shared memory; g_grid is not rewritten
+    b.cells = cells_range(q.cells, p, b0);
+    part = w.part + (size_t)2 * b0 * p->N;
+    b.part = part; b.Vz = p->Vz; b.N = p->N; b.P = n;
+  }
   DPC_TRY(launch_blur_xy(b, rx, kx, ry, ky, s));
   stage_mark(s);
+  if (q.cells) {
+    DPC_TRY(launch_pose_bwd_partials(
+        pa, b.cells, part, q.g_tr_pc ? q.g_tr_pc + b0 * N3 : nullptr, q.g_points + b0 * N3,
+        w.pose_partials + (size_t)b0 * pose_partial_blocks(p->N) * 8, w.counters + b0,
+        q.scale ? w.scale_partials + (size_t)b0 * drc_scale_partial_blocks(p->V) : nullptr,
+        drc_scale_partial_blocks(p->V), q.g_quat ? q.g_quat + b0 * 4 : nullptr,
+        (q.trans && q.g_trans) ? q.g_trans + b0 * 3 : nullptr,
+        (q.focal && q.g_focal) ? q.g_focal + b0 : nullptr,
+        (q.scale && q.g_scale) ? q.g_scale + b0 : nullptr, s));
+    stage_mark(s);
+    return DPC_OK;
+  }
   // gather + pose adjoint; the last block of each projection also reduces the partials
   DPC_TRY(launch_gather_pose_finalize(
       pa, g_grid, q.g_tr_pc ? q.g_tr_pc + b0 * N3 : nullptr, q.g_points + b0 * N3,
@@ -427,10 +476,11 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
 int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
                     const float *ty, int ky, const float *tz, int kz, const float *grid_b,
-                    const uint32_t *clamp_bits, const float *g_mask, const float *g_depth,
-                    const float *g_probs, const float *g_voxels, const float *g_tr_pc,
-                    float *g_grid, float *g_points, float *g_quat, float *g_trans, float *g_focal,
-                    float *g_scale, void *workspace, size_t workspace_bytes, void *stream) {
+                    const uint32_t *clamp_bits, const void *cells, const float *g_mask,
+                    const float *g_depth, const float *g_probs, const float *g_voxels,
+                    const float *g_tr_pc, float *g_grid, float *g_points, float *g_quat,
+                    float *g_trans, float *g_focal, float *g_scale, void *workspace,
+                    size_t workspace_bytes, void *stream) {
   DPC_TRY(check_params(p, true));
   DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
   DPC_REQUIRE(g_grid); DPC_REQUIRE(g_points);
@@ -440,7 +490,8 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
-                  g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale};
+                  g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
+                  const_cast<void *>(cells)};
   const int chunk = chunk_size(p);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   int rc = DPC_OK;
@@ -465,7 +516,8 @@ int dpc_project_profile(const dpc_params *p, const float *points, const float *q
                         const float *trans, const float *focal, const float *scale,
                         const float *tx, int kx, const float *ty, int ky, const float *tz, int kz,
                         int scatter_mode, float *tr_pc, float *grid_b, uint32_t *clamp_bits,
-                        float *mask, float *depth, const float *g_mask, const float *g_depth,
+                        void *cells, float *mask, float *depth, const float *g_mask,
+                        const float *g_depth,
                         float *g_grid, float *g_points, float *g_quat, float *g_trans,
                         float *g_focal, float *g_scale, void *workspace, size_t workspace_bytes,
                         void *stream, int iters, float *stage_ms_host) {
@@ -480,13 +532,14 @@ int dpc_project_profile(const dpc_params *p, const float *points, const float *q
     tl_stage_idx = 0;
     tl_force_single = true;   // whole batch per kernel, on the caller's stream
     rc = dpc_project_fwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, scatter_mode,
-                         tr_pc, grid_b, clamp_bits, mask, depth, nullptr, nullptr, workspace,
+                         tr_pc, grid_b, clamp_bits, cells, mask, depth, nullptr, nullptr, workspace,
                          workspace_bytes, stream);
     const int nf = tl_stage_idx;  // 5 events: start + 4 stages
     if (rc == DPC_OK)
       rc = dpc_project_bwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, grid_b,
-                           clamp_bits, g_mask, g_depth, nullptr, nullptr, nullptr, g_grid, g_points,
-                           g_quat, g_trans, g_focal, g_scale, workspace, workspace_bytes, stream);
+                           clamp_bits, scatter_mode == DPC_SCATTER_SORTED ? nullptr : cells, g_mask,
+                           g_depth, nullptr, nullptr, nullptr, g_grid, g_points, g_quat, g_trans,
+                           g_focal, g_scale, workspace, workspace_bytes, stream);
     const int nb = tl_stage_idx;  // + 5 events
     tl_stage_events = nullptr;
     tl_force_single = false;

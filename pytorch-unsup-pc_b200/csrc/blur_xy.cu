@@ -26,6 +26,17 @@
 // The backward (adjoint) is the same kernel: each zero-padded pass is the
 // transpose of itself with the taps reversed, the passes commute, and the
 // clamp gate is applied on the final store.
+//
+// POINTS mode (the whole-projection path): the plane never exists in global
+// memory as a raw grid.  Forward: the CTA scans the projection's z-cell bytes
+// (N bytes, L2-resident), and the ~2N/Vz points whose cell touches this plane
+// add their four in-plane trilinear weights to the shared-memory tile
+// (point_cloud_to.py:41-60, the eight index_put_ calls, split by plane) --
+// no memset, no global atomics, no load of a raw grid; clamp(raw,0,1) and the
+// raw<=1 bit mask are taken on the tile.  Backward: the masked dL/draw plane
+// stays in shared memory and the same scan gathers it at the touching points'
+// corners (IndexPutBackward, split by plane) into two per-point partials --
+// the gradient grid is never written or randomly re-read.
 #include "common.cuh"
 
 namespace dpc {
@@ -98,17 +109,34 @@ __device__ __forceinline__ float4 clamp01(float4 v) {
   return v;
 }
 
+// f(n, dz) for every point n of projection b whose trilinear cell touches
+// plane z: dz = 0 when z is the cell's lower plane (iz == z, weight 1 - rz),
+// dz = 1 when it is the upper one (iz == z - 1, weight rz).  The points are
+// binned by z cell (bin_points_kernel), so the ~2N/Vz touching points are ONE
+// contiguous range of the order array: no scan, no compaction, every lane busy.
+template <typename F>
+__device__ __forceinline__ void for_each_touching_point(const CellsView &cells, int b, int z,
+                                                        int N, int tid, int nthreads, F &&f) {
+  const uint32_t *bs = cells.binstart + (size_t)b * cells.zstride;
+  const uint32_t mid = __ldg(bs + z), hi = __ldg(bs + z + 1);
+  const uint32_t lo = z > 0 ? __ldg(bs + z - 1) : mid;
+  const uint32_t *order = cells.order + (size_t)b * N;
+  for (uint32_t i = lo + tid; i < hi; i += nthreads) f((int)__ldg(order + i), i < mid ? 1 : 0);
+}
+
 __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
   return (v.x <= 1.f ? 1u : 0u) | (v.y <= 1.f ? 2u : 0u) | (v.z <= 1.f ? 4u : 0u) |
          (v.w <= 1.f ? 8u : 0u);
 }
 
-template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT>
+template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT, bool POINTS>
 __global__ void __launch_bounds__(XYCfg<V, R>::THREADS, XYCfg<V, R>::MINB)
 blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                uint32_t *__restrict__ bits_out, const uint32_t *__restrict__ bits_in,
-               const Taps<R> kx, const Taps<R> ky) {
+               const Taps<R> kx, const Taps<R> ky, const CellsView cells,
+               float4 *__restrict__ part, int Vz, int N, int P) {
   using C = XYCfg<V, R>;
+  static_assert(!POINTS || (WRITE_BITS != MASK_OUT), "POINTS: forward (bits out) or backward (mask)");
   constexpr int HALF = C::RH / 2;
   extern __shared__ __align__(16) float2 smem2[];
   float2 *A2 = smem2;                  // [RH/2][S]  (row r, row r + RH/2), x padded by R
@@ -127,8 +155,51 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 
 #pragma unroll 1
   for (int h = 0; h < V / C::RH; ++h) {
+    if (POINTS && WRITE_BITS) {
+      // ---- build rows [h*RH, (h+1)*RH) of the raw plane from the touching points ----
+      const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
+      if (h > 0) {
+        for (int i = tid; i < HALF * C::S / 2; i += C::THREADS)
+          reinterpret_cast<float4 *>(A2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+      }
+      for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](int n, int dz) {
+        const uint4 r = __ldg(cells.rec + (size_t)pb * N + n);
+        const int iy = (int)(r.x >> 16), ix = (int)(r.x & 0xFFFFu);
+        const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
+        const float wz = dz ? rz : 1.f - rz;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int lr = iy + dy - h * C::RH;          // row inside this round
+          if (iy + dy >= V || lr < 0 || lr >= C::RH) continue;
+          const float wzy = wz * (dy ? ry : 1.f - ry);
+          float *cellp = reinterpret_cast<float *>(A2 + (lr % HALF) * C::S + R + ix) + lr / HALF;
+          atomicAdd(cellp, wzy * (1.f - rx));
+          if (ix + 1 < V) atomicAdd(cellp + 2, wzy * rx);
+        }
+      });
+      __syncthreads();
+      // clamp(raw, 0, 1) in place + the raw <= 1 bit mask (one ballot = one 32-voxel word)
+      for (int rp = tid >> 5; rp < HALF; rp += C::THREADS / 32) {
+        const int r0 = h * C::RH + rp, r1 = r0 + HALF;
+#pragma unroll
+        for (int q = 0; q < V / 32; ++q) {
+          float2 *e = A2 + rp * C::S + R + 32 * q + (tid & 31);
+          float2 v = *e;
+          const uint32_t b0 = __ballot_sync(0xffffffffu, v.x <= 1.f);
+          const uint32_t b1 = __ballot_sync(0xffffffffu, v.y <= 1.f);
+          v.x = fminf(fmaxf(v.x, 0.f), 1.f);
+          v.y = fminf(fmaxf(v.y, 0.f), 1.f);
+          *e = v;
+          if ((tid & 31) == 0) {
+            bits_out[plane * (V * V / 32) + (r0 * V) / 32 + q] = b0;
+            bits_out[plane * (V * V / 32) + (r1 * V) / 32 + q] = b1;
+          }
+        }
+      }
+    }
     // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
-    for (int i = tid; i < C::FILL_ITEMS; i += C::THREADS) {
+    for (int i = tid; i < ((POINTS && WRITE_BITS) ? 0 : C::FILL_ITEMS); i += C::THREADS) {
       const int rp = i / (V / 4), c4 = i % (V / 4);
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;
       float4 a = __ldg(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
@@ -185,10 +256,17 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #pragma unroll
   for (int t = 0; t < 2 * R + 1; ++t) k2[t] = bx_pack2(ky.k[t], ky.k[t]);
   float *dp = dst + plane * V * V;
+  // POINTS backward: the masked result goes to a natural-layout [y][x] tile --
+  // over the (then dead) window tile when one round covers the plane, else
+  // into its own region behind the tiles
+  constexpr bool GATHER = POINTS && MASK_OUT;
+  constexpr bool G_OVER_TILE = (C::YTASKS == C::THREADS);
+  float *G = reinterpret_cast<float *>(G_OVER_TILE ? smem2 : smem2 + C::TILE_LINES * C::S);
   for (int task = tid; task < C::YTASKS; task += C::THREADS) {
     const int cp = task % (V / 2), y0 = (task / (V / 2)) * C::J;
     u64 acc[C::J];
     window_fma2<R, C::J, C::W2>(B2 + cp * C::S + y0, k2, acc);
+    if (GATHER && G_OVER_TILE) __syncthreads();   // every window is in registers
 #pragma unroll
     for (int j = 0; j < C::J; ++j) {
       float lo, hi;
@@ -199,8 +277,30 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
         lo = ((wbits >> sh) & 1u) ? lo : 0.f;
         hi = ((wbits >> (sh + 1)) & 1u) ? hi : 0.f;
       }
-      *reinterpret_cast<float2 *>(dp + (y0 + j) * V + 2 * cp) = make_float2(lo, hi);
+      if (GATHER)
+        *reinterpret_cast<float2 *>(G + (y0 + j) * V + 2 * cp) = make_float2(lo, hi);
+      else
+        *reinterpret_cast<float2 *>(dp + (y0 + j) * V + 2 * cp) = make_float2(lo, hi);
     }
+  }
+  if (GATHER) {
+    __syncthreads();
+    const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
+    for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](int n, int dz) {
+      const uint4 r = __ldg(cells.rec + (size_t)pb * N + n);
+      const int iy = (int)(r.x >> 16), ix = (int)(r.x & 0xFFFFu);
+      const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
+      const bool y1 = iy + 1 < V, x1 = ix + 1 < V;   // out-of-range corners carry no gradient
+      const float *g0 = G + iy * V + ix;
+      const float G00 = g0[0], G01 = x1 ? g0[1] : 0.f;
+      const float G10 = y1 ? g0[V] : 0.f, G11 = (y1 && x1) ? g0[V + 1] : 0.f;
+      const float wz = dz ? rz : 1.f - rz, wy0 = 1.f - ry, wx0 = 1.f - rx;
+      // adjoint of the trilinear weights restricted to this plane
+      const float sz = wy0 * (wx0 * G00 + rx * G01) + ry * (wx0 * G10 + rx * G11);
+      const float sy = wz * (wx0 * (G10 - G00) + rx * (G11 - G01));
+      const float sx = wz * (wy0 * (G01 - G00) + ry * (G11 - G10));
+      part[((size_t)dz * P + pb) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
+    });
   }
 }
 
@@ -210,26 +310,37 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
   using C = XYCfg<V, R>;
   const Taps<R> KX = make_taps<R>(tx, kx), KY = make_taps<R>(ty, ky);
   dim3 g(a.planes), t(C::THREADS);
-#define DPC_LAUNCH_XY(CL, WB, MO)                                                              \
+#define DPC_LAUNCH_XY(CL, WB, MO, PT)                                                          \
   do {                                                                                         \
+    /* the gather tile lives behind the window tiles when it cannot overlay them */            \
+    const size_t smem = C::SMEM + ((PT && MO && C::YTASKS != C::THREADS) ? V * V * 4 : 0);     \
     static bool attr_done = false;                                                             \
     if (!attr_done) {                                                                          \
-      cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO>,                                   \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);         \
+      cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT>,                               \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
       attr_done = true;                                                                        \
     }                                                                                          \
-    blur_xy_kernel<V, R, CL, WB, MO><<<g, t, C::SMEM, s>>>(a.src, a.dst, a.bits_out, a.bits_in, \
-                                                           KX, KY);                            \
+    blur_xy_kernel<V, R, CL, WB, MO, PT><<<g, t, smem, s>>>(a.src, a.dst, a.bits_out,          \
+                                                            a.bits_in, KX, KY, a.cells, a.part, \
+                                                            a.Vz, a.N, a.P);                   \
   } while (0)
+  const bool points = a.cells.cellz != nullptr;
+  if (points && (a.Vz < 1 || a.N < 1 || a.P < 1 || (!a.bits_in && !a.bits_out) ||
+                 (a.bits_in && !a.part))) {
+    set_error("blur_xy: plane-local scatter/gather needs Vz, N, P and bits (and part backward)");
+    return DPC_ERR_ARG;
+  }
   if (a.bits_in) {
-    DPC_LAUNCH_XY(false, false, true);
+    if (points) DPC_LAUNCH_XY(false, false, true, true);
+    else DPC_LAUNCH_XY(false, false, true, false);
   } else if (a.bits_out) {
     if (!a.clamp_in) { set_error("blur_xy: bits_out requires clamp_in"); return DPC_ERR_ARG; }
-    DPC_LAUNCH_XY(true, true, false);
+    if (points) DPC_LAUNCH_XY(true, true, false, true);
+    else DPC_LAUNCH_XY(true, true, false, false);
   } else if (a.clamp_in) {
-    DPC_LAUNCH_XY(true, false, false);
+    DPC_LAUNCH_XY(true, false, false, false);
   } else {
-    DPC_LAUNCH_XY(false, false, false);
+    DPC_LAUNCH_XY(false, false, false, false);
   }
 #undef DPC_LAUNCH_XY
   return check_launch("blur_xy");

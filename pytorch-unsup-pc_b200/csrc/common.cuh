@@ -53,6 +53,52 @@ struct PoseArgs {
   double cam_dist, focal_const;
 };
 
+// Per-point cell records (saved by the forward for the backward): the grid cell
+// and trilinear fractions of every point, derived ONCE from the fp64 pose so
+// that the plane-local scatter (forward) and gather (backward) can never
+// disagree on a cell, plus the points of every projection binned by z cell so
+// that a plane's CTA reads the points touching it as one contiguous range.
+//   cellz    [P][Npad] u8  : z cell index (kCellNone = point outside the frustum;
+//                            padding bytes up to Npad, a multiple of 16, are kCellNone)
+//   rec      [P][N] uint4  : {iy << 16 | ix, bits(rz), bits(ry), bits(rx)}
+//   order    [P][N] u32    : point indices sorted by z cell (valid points only)
+//   binstart [P][zstride]  : order[binstart[z] .. binstart[z+1]) = points with iz == z
+constexpr unsigned kCellNone = 255u;
+struct CellsView {
+  uint8_t *cellz;
+  uint4 *rec;
+  uint32_t *order;
+  uint32_t *binstart;
+  int Npad, zstride;
+};
+inline int cells_npad(int N) { return (N + 15) & ~15; }
+inline int cells_zstride(int Vz) { return (Vz + 1 + 3) & ~3; }
+inline size_t cells_z_bytes(int P, int N) { return ((size_t)P * cells_npad(N) + 255) & ~(size_t)255; }
+inline size_t cells_bytes(int P, int N, int Vz) {
+  return cells_z_bytes(P, N) + (size_t)P * N * (sizeof(uint4) + sizeof(uint32_t)) +
+         (size_t)P * cells_zstride(Vz) * sizeof(uint32_t);
+}
+inline CellsView cells_view(void *base, int P, int N, int Vz) {
+  CellsView v;
+  v.cellz = (uint8_t *)base;
+  v.rec = (uint4 *)((char *)base + cells_z_bytes(P, N));
+  v.order = (uint32_t *)(v.rec + (size_t)P * N);
+  v.binstart = v.order + (size_t)P * N;
+  v.Npad = cells_npad(N);
+  v.zstride = cells_zstride(Vz);
+  return v;
+}
+// pose -> tr_pc (NULL ok) + cell records
+int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, cudaStream_t s);
+// pose adjoint fed by the two per-plane partial gathers of the fused blur-XY
+// adjoint (part[dz][P][N] float4 = dL/du contribution of the corners in plane
+// iz + dz) + fused last-block finalize
+int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const float4 *part,
+                             const float *g_trpc, float *g_points, double *partials,
+                             int *counters, const float *scale_partials, int scale_blocks,
+                             float *g_quat, float *g_trans, float *g_focal, float *g_scale,
+                             cudaStream_t s);
+
 // pose (+ optional scatter into `grid`): tr_pc may be NULL when grid != NULL.
 int launch_pose_scatter(const PoseArgs &a, float *tr_pc, float *grid, cudaStream_t s);
 // scatter of given tr_pc (fp32) into grid (atomic)
@@ -88,6 +134,16 @@ struct BlurXYArgs {
   const uint32_t *bits_in; // backward: multiply the output by the mask (NULL ok)
   int planes, V;
   bool clamp_in;           // clamp(src,0,1) on load
+  // Plane-local scatter / gather (cells.cellz != NULL; needs Vz and N):
+  //  forward  (bits_out != NULL): src is ignored, every plane is BUILT in shared
+  //           memory from the points whose cell touches it (no memset, no global
+  //           atomics, no read of a raw grid);
+  //  backward (bits_in != NULL):  dst is ignored, the masked result stays in
+  //           shared memory and is gathered at the touching points' corners into
+  //           part[dz][P][N] (no write and no random re-read of a gradient grid).
+  CellsView cells = {nullptr, nullptr, nullptr, nullptr, 0, 0};
+  float4 *part = nullptr;
+  int Vz = 0, N = 0, P = 0;
 };
 int launch_blur_xy(const BlurXYArgs &a, const float *tx, int kx, const float *ty, int ky,
                    cudaStream_t s);

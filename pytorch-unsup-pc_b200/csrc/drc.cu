@@ -73,6 +73,25 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// clamp of both halves (min/max have no packed form)
+__device__ __forceinline__ u64 clamp2(u64 x, float lo, float hi) {
+  float a, b;
+  unpack2(x, a, b);
+  return pack2(fminf(fmaxf(a, lo), hi), fminf(fmaxf(b, lo), hi));
+}
+// keep a half of g where the matching halves of x and y are equal, else 0
+__device__ __forceinline__ u64 keep_if_equal2(u64 g, u64 x, u64 y) {
+  float g0, g1, x0, x1, y0, y1;
+  unpack2(g, g0, g1);
+  unpack2(x, x0, x1);
+  unpack2(y, y0, y1);
+  return pack2(x0 == y0 ? g0 : 0.f, x1 == y1 ? g1 : 0.f);
+}
 
 // Ring length for a tap radius.  Backward (fed from shared memory): 2R+1 taps
 // + 3.  Forward (fed from global memory): 2R+1 taps + the load-ahead distance
@@ -88,6 +107,10 @@ struct RayConst {
   float inv_z, depth0, max_depth, exp_clip;
   float lo_s, hi_s;   // clamp(s*B, 0, 1) bounds; +-inf when there is no scaling factor
   float lo_c, hi_c;   // DRC clip bounds;        +-inf for the product form
+  // clamp(clamp(x, lo_s, hi_s), lo_c, hi_c) == clamp(x, lo, hi) with the nested
+  // bounds below, and BOTH clamp gates are open exactly when the clamp left x
+  // unchanged (torch's clamp backward passes the closed interval)
+  float lo, hi;
   int flip_y, has_scale;
 };
 
@@ -103,6 +126,8 @@ static RayConst make_ray_const(const DrcArgs &a) {
   c.hi_s = c.has_scale ? 1.f : INFINITY;
   c.lo_c = a.logsum ? a.clip : -INFINITY;
   c.hi_c = a.logsum ? 1.0f - a.clip : INFINITY;
+  c.lo = fmaxf(c.lo_s, c.lo_c);
+  c.hi = fminf(c.hi_s, c.hi_c);
   c.flip_y = a.flip_y;
   return c;
 }
@@ -137,7 +162,7 @@ __device__ __forceinline__ void pair_index(const RayConst &c, int threads, int &
   out_idx = b * VV + yo * V + x;
 }
 
-// Streams the pair blurZ(col)_z, z = 0..Vz-1, to sink(j, z, lo, hi); j is the
+// Streams the pair blurZ(col)_z, z = 0..Vz-1, to sink(j, z, pair); j is the
 // compile-time position inside the current block of L steps.  SAVE writes the
 // blurred pair back over the input column (bs may alias col).
 template <int V, int R, bool SAVE, typename Sink>
@@ -164,9 +189,7 @@ __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int 
             (z + AHEAD < Vz) ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
         const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
         if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = b2;
-        float lo, hi;
-        unpack2(b2, lo, hi);
-        sink(j, z, lo, hi);
+        sink(j, z, b2);
       }
     }
     col += (size_t)L * VV;
@@ -187,38 +210,37 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   pair_index<V>(c, kFwdThreads, b, yx, oi);
   const size_t col0 = (size_t)b * c.Vz * VV + yx;
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
-  float T[2] = {1.f, 1.f}, m[2] = {0.f, 0.f}, d[2] = {0.f, 0.f};
+  const u64 s2 = pack2(s, s), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
+  const u64 ec2 = pack2(c.exp_clip, c.exp_clip);
+  u64 T2 = one2, m2 = 0, d2 = 0;   // transmittance, mask and depth sums of the two rays
   float kf = 0.f;
   float *vx = (EXTRA && voxels) ? voxels + col0 : nullptr;
   float *pr = (EXTRA && probs) ? probs + oi : nullptr;
   const size_t pstride = (size_t)c.P * VV;
   stream_blur_z2<V, R, SAVE>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
-                             [&](int j, int z, float b0, float b1) {
+                             [&](int j, int z, u64 b2) {
     const float psi = fmaf(kf, c.inv_z, c.depth0);
     kf += 1.f;
-    const float bz[2] = {b0, b1};
-    float vox[2], p[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      vox[h] = fminf(fmaxf(s * bz[h], c.lo_s), c.hi_s);
-      const float v = fminf(fmaxf(vox[h], c.lo_c), c.hi_c);
-      p[h] = v * T[h];
-      if (j == 0 && z == 0) p[h] *= c.exp_clip;   // only block position 0 can be z == 0
-      m[h] += p[h];
-      d[h] = fmaf(psi, p[h], d[h]);
-      T[h] *= (1.f - v);
-    }
+    const u64 sb2 = mul2(s2, b2);
+    u64 v2;
     if (EXTRA) {
-      if (vx) { *reinterpret_cast<float2 *>(vx) = make_float2(vox[0], vox[1]); vx += VV; }
-      if (pr) { *reinterpret_cast<float2 *>(pr) = make_float2(p[0], p[1]); pr += pstride; }
+      const u64 vox2 = clamp2(sb2, c.lo_s, c.hi_s);
+      v2 = clamp2(vox2, c.lo_c, c.hi_c);
+      if (vx) { *reinterpret_cast<u64 *>(vx) = vox2; vx += VV; }
+    } else {
+      v2 = clamp2(sb2, c.lo, c.hi);   // the two nested clamps in one
     }
+    u64 p2 = mul2(v2, T2);
+    if (j == 0 && z == 0) p2 = mul2(p2, ec2);   // only block position 0 can be z == 0
+    m2 = add2(m2, p2);
+    d2 = fma2(pack2(psi, psi), p2, d2);
+    T2 = mul2(T2, fma2(v2, neg2, one2));         // T *= (1 - v)
+    if (EXTRA && pr) { *reinterpret_cast<u64 *>(pr) = p2; pr += pstride; }
   });
-  const float pz0 = c.exp_clip * T[0], pz1 = c.exp_clip * T[1];
-  if (EXTRA && pr) *reinterpret_cast<float2 *>(pr) = make_float2(pz0, pz1);
-  *reinterpret_cast<float2 *>(mask + oi) = make_float2(m[0], m[1]);
-  if (depth)
-    *reinterpret_cast<float2 *>(depth + oi) =
-        make_float2(fmaf(c.max_depth, pz0, d[0]), fmaf(c.max_depth, pz1, d[1]));
+  const u64 pz2 = mul2(ec2, T2);
+  if (EXTRA && pr) *reinterpret_cast<u64 *>(pr) = pz2;
+  *reinterpret_cast<u64 *>(mask + oi) = m2;
+  if (depth) *reinterpret_cast<u64 *>(depth + oi) = fma2(pack2(c.max_depth, c.max_depth), pz2, d2);
 }
 
 template <int V, int R, bool EXTRA>
@@ -241,33 +263,33 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
   const int nblk = (c.Vz + L - 1) / L;
 
-  auto occupancy = [&](float bz, float &sb, float &vox) -> float {
-    sb = s * bz;
-    vox = fminf(fmaxf(sb, c.lo_s), c.hi_s);
-    return fminf(fmaxf(vox, c.lo_c), c.hi_c);
+  const u64 s2 = pack2(s, s), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
+  const u64 ec2 = pack2(c.exp_clip, c.exp_clip);
+  u64 *sB2 = reinterpret_cast<u64 *>(sB);
+  u64 *sC2 = reinterpret_cast<u64 *>(sC);
+  // 1 - v of the pair, v = clamp(clamp(s B, lo_s, hi_s), lo_c, hi_c) = clamp(s B, lo, hi)
+  auto one_minus_v = [&](u64 b2) -> u64 {
+    return fma2(clamp2(mul2(s2, b2), c.lo, c.hi), neg2, one2);
   };
 
   // ---- sweep 1: stage the column pair, checkpoint the transmittance ----
   {
     const float *ld = bgrid + col0;
-    float T0 = 1.f, T1 = 1.f;
+    u64 T2 = one2;
 #pragma unroll 1
     for (int bi = 0; bi < nblk; ++bi) {
-      sC[bi * kBwdThreads] = make_float2(T0, T1);
-      float2 vals[L];
+      sC2[bi * kBwdThreads] = T2;
+      u64 vals[L];
 #pragma unroll
       for (int j = 0; j < L; ++j)
-        vals[j] = (bi * L + j < c.Vz) ? __ldg(reinterpret_cast<const float2 *>(ld + (size_t)j * VV))
-                                      : make_float2(0.f, 0.f);
+        vals[j] = (bi * L + j < c.Vz) ? __ldg(reinterpret_cast<const u64 *>(ld + (size_t)j * VV)) : 0ull;
       ld += (size_t)L * VV;
 #pragma unroll
       for (int j = 0; j < L; ++j) {
         const int z = bi * L + j;
         if (z < c.Vz) {
-          sB[z * kBwdThreads] = vals[j];
-          float sb, vox;
-          T0 *= (1.f - occupancy(vals[j].x, sb, vox));
-          T1 *= (1.f - occupancy(vals[j].y, sb, vox));
+          sB2[z * kBwdThreads] = vals[j];
+          T2 = mul2(T2, one_minus_v(vals[j]));
         }
       }
     }
@@ -276,15 +298,11 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   const float2 gm = g_mask ? __ldg(reinterpret_cast<const float2 *>(g_mask + oi)) : make_float2(0.f, 0.f);
   const float2 gd = g_depth ? __ldg(reinterpret_cast<const float2 *>(g_depth + oi)) : make_float2(0.f, 0.f);
   const size_t pstride = (size_t)c.P * VV;
-  float D[2] = {c.max_depth * gd.x, c.max_depth * gd.y};
-  if (EXTRA && g_probs) {
-    const float2 gz = __ldg(reinterpret_cast<const float2 *>(g_probs + (size_t)c.Vz * pstride + oi));
-    D[0] += gz.x;
-    D[1] += gz.y;
-  }
-  D[0] *= c.exp_clip;
-  D[1] *= c.exp_clip;
-  float ds = 0.f;
+  u64 D2 = pack2(c.max_depth * gd.x, c.max_depth * gd.y);
+  if (EXTRA && g_probs)
+    D2 = add2(D2, __ldg(reinterpret_cast<const u64 *>(g_probs + (size_t)c.Vz * pstride + oi)));
+  D2 = mul2(D2, ec2);
+  u64 ds2 = 0;
   u64 k2[W];
 #pragma unroll
   for (int t = 0; t < W; ++t) k2[t] = pack2(kz.k[t], kz.k[t]);
@@ -296,18 +314,13 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   for (int bi = nblk - 1; bi >= 0; --bi) {
     const int z0 = bi * L;
     // re-expand T_k inside the block from its checkpoint
-    float2 tseg[L];
+    u64 tseg[L];
     {
-      float2 T = sC[bi * kBwdThreads];
+      u64 T2 = sC2[bi * kBwdThreads];
 #pragma unroll
       for (int j = 0; j < L; ++j) {
-        tseg[j] = T;
-        if (z0 + j < c.Vz) {
-          const float2 bz = sB[(z0 + j) * kBwdThreads];
-          float sb, vox;
-          T.x *= (1.f - occupancy(bz.x, sb, vox));
-          T.y *= (1.f - occupancy(bz.y, sb, vox));
-        }
+        tseg[j] = T2;
+        if (z0 + j < c.Vz) T2 = mul2(T2, one_minus_v(sB2[(z0 + j) * kBwdThreads]));
       }
     }
     // block-base pointers; inside the block every offset is an immediate
@@ -318,35 +331,31 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
 #pragma unroll
     for (int j = L - 1; j >= 0; --j) {
       const int k = z0 + j;
-      float gB[2] = {0.f, 0.f};
+      u64 gB2 = 0;
       if (k < c.Vz) {
-        const float2 bz2 = sB[k * kBwdThreads];
-        const float bz[2] = {bz2.x, bz2.y}, Tk[2] = {tseg[j].x, tseg[j].y};
-        const float gmh[2] = {gm.x, gm.y}, gdh[2] = {gd.x, gd.y};
+        const u64 b2 = sB2[k * kBwdThreads];
+        const u64 sb2 = mul2(s2, b2);
         const float psi = fmaf(kf0 + (float)j, c.inv_z, c.depth0);
-        float2 gp2 = make_float2(0.f, 0.f), gv2 = make_float2(0.f, 0.f);
+        u64 a2 = pack2(fmaf(psi, gd.x, gm.x), fmaf(psi, gd.y, gm.y));
+        if (EXTRA && gpr) a2 = add2(a2, __ldg(reinterpret_cast<const u64 *>(gpr + (size_t)j * pstride)));
+        if (j == 0 && k == 0) a2 = mul2(a2, ec2);
+        u64 v2, gv2;
         if (EXTRA) {
-          if (gpr) gp2 = __ldg(reinterpret_cast<const float2 *>(gpr + (size_t)j * pstride));
-          if (gvx) gv2 = __ldg(reinterpret_cast<const float2 *>(gvx + (size_t)j * VV));
+          // g_voxels enters between the two clamp gates: keep them separate
+          const u64 vox2 = clamp2(sb2, c.lo_s, c.hi_s);
+          v2 = clamp2(vox2, c.lo_c, c.hi_c);
+          gv2 = keep_if_equal2(mul2(tseg[j], fma2(D2, neg2, a2)), v2, vox2);
+          if (gvx) gv2 = add2(gv2, __ldg(reinterpret_cast<const u64 *>(gvx + (size_t)j * VV)));
+          gv2 = keep_if_equal2(gv2, vox2, sb2);
+        } else {
+          v2 = clamp2(sb2, c.lo, c.hi);
+          gv2 = keep_if_equal2(mul2(tseg[j], fma2(D2, neg2, a2)), v2, sb2);   // T (a - D), gated
         }
-        const float gph[2] = {gp2.x, gp2.y}, gvh[2] = {gv2.x, gv2.y};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float sb, vox;
-          const float v = occupancy(bz[h], sb, vox);
-          float a = fmaf(psi, gdh[h], gmh[h]);
-          if (EXTRA) a += gph[h];
-          if (j == 0 && k == 0) a *= c.exp_clip;
-          float gv = Tk[h] * (a - D[h]);
-          D[h] = fmaf(a, v, (1.f - v) * D[h]);
-          gv = (vox >= c.lo_c && vox <= c.hi_c) ? gv : 0.f;
-          if (EXTRA) gv += gvh[h];
-          gv = (sb >= c.lo_s && sb <= c.hi_s) ? gv : 0.f;
-          ds = fmaf(gv, bz[h], ds);
-          gB[h] = gv * s;
-        }
+        D2 = fma2(a2, v2, mul2(fma2(v2, neg2, one2), D2));   // D = a v + (1 - v) D
+        ds2 = fma2(gv2, b2, ds2);
+        gB2 = mul2(gv2, s2);
       }
-      ring[j] = pack2(gB[0], gB[1]);
+      ring[j] = gB2;
       // out[z] = sum_t kz[2R-t] * in[k + t], z = k + R   (adjoint = reversed taps);
       // in[k + t] sits in slot (j + t) % L
       if (k + R < c.Vz)
@@ -366,6 +375,9 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   // ---- dL/dscale: fixed-order block reduction ----
   if (scale_partials) {
     __shared__ float red[kBwdThreads / 32];
+    float ds, ds_hi;
+    unpack2(ds2, ds, ds_hi);
+    ds += ds_hi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ds += __shfl_down_sync(0xffffffffu, ds, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
@@ -386,7 +398,7 @@ blur_z_kernel(const float *src, float *dst, int Vz, const Taps<R> kz) {
   const int pair = blockIdx.x * kFwdThreads + threadIdx.x;
   const int b = pair / (VV / 2), yx = 2 * (pair - b * (VV / 2));
   const size_t col0 = (size_t)b * Vz * VV + yx;
-  stream_blur_z2<V, R, true>(src + col0, dst + col0, Vz, kz, [](int, int, float, float) {});
+  stream_blur_z2<V, R, true>(src + col0, dst + col0, Vz, kz, [](int, int, u64) {});
 }
 
 __global__ void __launch_bounds__(128)

@@ -69,6 +69,108 @@ pose_scatter_kernel(PoseArgs a, float *__restrict__ tr_pc, float *__restrict__ g
   }
 }
 
+// Pose + cell records (the forward of the plane-local scatter path): tr_pc for
+// the caller, {z cell, (iy, ix), fractions} for the blur-XY kernels that build
+// each Z-plane in shared memory.  Threads n in [N, Npad) write the padding.
+template <bool WRITE_TRPC>
+__global__ void __launch_bounds__(kPoseThreads)
+pose_cells_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  if (n >= cells.Npad) return;
+  uint8_t *cz = cells.cellz + (size_t)b * cells.Npad;
+  if (n >= a.N) {
+    cz[n] = (uint8_t)kCellNone;
+    return;
+  }
+  const Quat q = load_quat(a.quat + 4 * b);
+  const bool has_t = a.trans != nullptr;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  if (has_t) {
+    t0 = a.trans[3 * b];
+    t1 = a.trans[3 * b + 1];
+    t2 = a.trans[3 * b + 2];
+  }
+  const double f = a.focal ? (double)a.focal[b] : a.focal_const;
+  const size_t pi = ((size_t)b * a.N + n) * 3;
+  const PosePoint pp = pose_point(q, a.points[pi], a.points[pi + 1], a.points[pi + 2], has_t, t0,
+                                  t1, t2, f, a.cam_dist);
+  if (WRITE_TRPC) {
+    tr_pc[pi] = (float)pp.u0;
+    tr_pc[pi + 1] = (float)pp.u1;
+    tr_pc[pi + 2] = (float)pp.u2;
+  }
+  const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
+  cz[n] = (uint8_t)(c.valid ? (unsigned)c.iz : kCellNone);
+  if (c.valid)
+    cells.rec[(size_t)b * a.N + n] =
+        make_uint4(((unsigned)c.iy << 16) | (unsigned)c.ix, __float_as_uint((float)c.rz),
+                   __float_as_uint((float)c.ry), __float_as_uint((float)c.rx));
+}
+
+// Counting sort of one projection's points by z cell (one CTA per projection):
+// shared-memory histogram of the z-cell bytes, exclusive scan, placement with
+// shared-memory cursors.  The order inside a bin is arbitrary (the consumers
+// accumulate with atomics or write per-point results), the bins are exact.
+constexpr int kBinThreads = 1024;
+constexpr int kMaxBins = 192;
+__global__ void __launch_bounds__(kBinThreads)
+bin_points_kernel(CellsView cells, int N, int Vz) {
+  __shared__ unsigned hist[kMaxBins + 1];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const uint4 *cz = reinterpret_cast<const uint4 *>(cells.cellz + (size_t)b * cells.Npad);
+  uint32_t *order = cells.order + (size_t)b * N;
+  for (int i = tid; i <= Vz; i += kBinThreads) hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < cells.Npad / 16; i += kBinThreads) {
+    const uint4 w = __ldg(cz + i);
+    const unsigned words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const unsigned c = (words[k / 4] >> (8 * (k % 4))) & 0xFFu;
+      if (c != kCellNone) atomicAdd(&hist[c], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // exclusive scan of Vz (<= 192) counts by one warp, 7 bins per lane
+    constexpr int PER = (kMaxBins + 1 + 31) / 32;   // covers z == Vz, the total
+    unsigned v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int z = tid * PER + k;
+      v[k] = z < Vz ? hist[z] : 0u;
+      sum += v[k];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += t;
+    }
+    unsigned run = incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int z = tid * PER + k;
+      if (z <= Vz) {
+        hist[z] = run;                                        // becomes the bin cursor
+        cells.binstart[(size_t)b * cells.zstride + z] = run;  // z == Vz: the total
+      }
+      run += v[k];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < cells.Npad / 16; i += kBinThreads) {
+    const uint4 w = __ldg(cz + i);
+    const unsigned words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const unsigned c = (words[k / 4] >> (8 * (k % 4))) & 0xFFu;
+      if (c != kCellNone) order[atomicAdd(&hist[c], 1u)] = (uint32_t)(16 * i + k);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kPoseThreads)
 scatter_trpc_kernel(const float *__restrict__ tr_pc, int N, int Vz, int V,
                     float *__restrict__ grid) {
@@ -201,7 +303,8 @@ __global__ void finalize_kernel(PoseArgs a, FinalizeArgs f) {
 __global__ void __launch_bounds__(kPoseThreads)
 gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
                        const float *__restrict__ g_trpc, float *__restrict__ g_points,
-                       double *__restrict__ partials, int *__restrict__ counters, FinalizeArgs fin) {
+                       double *__restrict__ partials, int *__restrict__ counters, FinalizeArgs fin,
+                       CellsView cells, const float4 *__restrict__ part) {
   const int b = blockIdx.y;
   const int n = blockIdx.x * kPoseThreads + threadIdx.x;
   const Quat q = load_quat(a.quat + 4 * b);
@@ -220,7 +323,24 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     const PosePoint pp = pose_point(q, (float)p0, (float)p1, (float)p2, has_t, t0, t1, t2, f,
                                     a.cam_dist);
     double gu0 = 0, gu1 = 0, gu2 = 0;
-    if (g_grid) {
+    if (part) {
+      // the blur-XY adjoint already gathered the corners plane by plane:
+      // part[0] = plane iz, part[1] = plane iz + 1 (absent when iz + 1 == Vz)
+      const unsigned iz = cells.cellz[(size_t)b * cells.Npad + n];
+      if (iz != kCellNone) {
+        const size_t idx = (size_t)b * a.N + n;
+        float4 s0 = __ldg(part + idx);
+        if ((int)iz + 1 < a.Vz) {
+          const float4 s1 = __ldg(part + (size_t)a.P * a.N + idx);
+          s0.x += s1.x;
+          s0.y += s1.y;
+          s0.z += s1.z;
+        }
+        gu0 = (double)s0.x * (double)(a.Vz - 1);
+        gu1 = (double)s0.y * (double)(a.V - 1);
+        gu2 = (double)s0.z * (double)(a.V - 1);
+      }
+    } else if (g_grid) {
       const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
       if (c.valid) gather_cell(c, g_grid + (size_t)b * a.Vz * a.V * a.V, a.Vz, a.V, gu0, gu1, gu2);
     }
@@ -313,7 +433,7 @@ int launch_gather_pose_bwd(const PoseArgs &a, const float *g_grid, const float *
                            float *g_points, double *partials, cudaStream_t s) {
   dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
   gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, nullptr,
-                                         FinalizeArgs{});
+                                         FinalizeArgs{}, CellsView{nullptr, nullptr, nullptr, nullptr, 0, 0}, nullptr);
   return check_launch("gather_pose_bwd");
 }
 
@@ -324,8 +444,33 @@ int launch_gather_pose_finalize(const PoseArgs &a, const float *g_grid, const fl
   dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
   FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
                  g_quat, g_trans, g_focal, g_scale};
-  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, counters, f);
+  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, counters, f,
+                                         CellsView{nullptr, nullptr, nullptr, nullptr, 0, 0}, nullptr);
   return check_launch("gather_pose_finalize");
+}
+
+int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const float4 *part,
+                             const float *g_trpc, float *g_points, double *partials,
+                             int *counters, const float *scale_partials, int scale_blocks,
+                             float *g_quat, float *g_trans, float *g_focal, float *g_scale,
+                             cudaStream_t s) {
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
+                 g_quat, g_trans, g_focal, g_scale};
+  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, nullptr, g_trpc, g_points, partials, counters, f,
+                                         cells, part);
+  return check_launch("pose_bwd_partials");
+}
+
+int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, cudaStream_t s) {
+  dim3 g((cells.Npad + kPoseThreads - 1) / kPoseThreads, a.P), t(kPoseThreads);
+  if (a.Vz > kMaxBins) { set_error("pose_cells: vox_size_z %d > %d", a.Vz, kMaxBins); return DPC_ERR_ARG; }
+  if (tr_pc)
+    pose_cells_kernel<true><<<g, t, 0, s>>>(a, tr_pc, cells);
+  else
+    pose_cells_kernel<false><<<g, t, 0, s>>>(a, tr_pc, cells);
+  bin_points_kernel<<<a.P, kBinThreads, 0, s>>>(cells, a.N, a.Vz);
+  return check_launch("pose_cells");
 }
 
 int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, const float *g_grid,

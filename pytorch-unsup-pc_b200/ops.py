@@ -95,15 +95,18 @@ def _workspace(params, device):
 class ProjectFn(torch.autograd.Function):
     """pointcloud_project_fast (point_cloud_to.py:191-263) as ONE op.
 
-    forward : memset + pose/scatter + blur XY (in place) + blur Z/DRC  (4 launches)
-    backward: DRC reverse scan/blur Z adjoint + blur XY adjoint + gather/pose
-              adjoint with fused final reductions                      (3 launches)
-    Saved for backward: the inputs, the blurred grid and a 1-bit clamp mask.
+    forward : pose + cell records, plane scatter + blur XY, blur Z/DRC   (3 launches)
+    backward: DRC reverse scan/blur Z adjoint, blur XY adjoint + plane gather,
+              pose adjoint with fused final reductions                   (3 launches)
+    (``plane_local=False`` or the deterministic mode: memset + global scatter
+    forward, grid gather backward.)
+    Saved for backward: the inputs, the blurred grid, a 1-bit clamp mask and
+    the per-point cell records.
     """
 
     @staticmethod
     def forward(ctx, points, quat, trans, focal, scale, params, taps, want_voxels, want_probs,
-                mode):
+                mode, plane_local=True):
         lib = _lib.load()
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
@@ -115,15 +118,20 @@ class ProjectFn(torch.autograd.Function):
         depth = torch.empty(P, V, V, **f32)
         voxels = torch.empty(P, Vz, V, V, **f32) if want_voxels else None
         probs = torch.empty(Vz + 1, P, V, V, **f32) if want_probs else None
+        # per-point cell records: the plane-local scatter/gather path (default mode)
+        cells = None
+        if int(mode) == _lib.SCATTER_ATOMIC and plane_local:
+            cells = torch.empty(lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8,
+                                device=dev)
         ws = _workspace(params, dev)
         with torch.cuda.device(dev):
             st = lib.dpc_project_fwd(
                 ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
                 _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), _ptr(grid_b), _ptr(bits),
-                _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws), ws.numel(),
-                _stream(dev))
+                _ptr(cells), _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws),
+                ws.numel(), _stream(dev))
         _lib.check(st, "project_fwd")
-        ctx.save_for_backward(points, quat, trans, focal, scale, grid_b, bits)
+        ctx.save_for_backward(points, quat, trans, focal, scale, grid_b, bits, cells)
         ctx.params, ctx.taps = params, taps
         ctx.set_materialize_grads(False)
         return mask, depth, tr_pc, voxels, probs
@@ -131,7 +139,7 @@ class ProjectFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mask, g_depth, g_trpc, g_voxels, g_probs):
         lib = _lib.load()
-        points, quat, trans, focal, scale, grid_b, bits = ctx.saved_tensors
+        points, quat, trans, focal, scale, grid_b, bits, cells = ctx.saved_tensors
         params = ctx.params
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
@@ -151,12 +159,12 @@ class ProjectFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = lib.dpc_project_bwd(
                 ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
-                _ptr(scale), *_tap_args(ctx.taps), _ptr(grid_b), _ptr(bits), _ptr(g_mask),
-                _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid),
+                _ptr(scale), *_tap_args(ctx.taps), _ptr(grid_b), _ptr(bits), _ptr(cells),
+                _ptr(g_mask), _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid),
                 _ptr(g_points), _ptr(g_quat), _ptr(g_trans), _ptr(g_focal), _ptr(g_scale),
                 _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(st, "project_bwd")
-        return (g_points, g_quat, g_trans, g_focal, g_scale, None, None, None, None, None)
+        return (g_points, g_quat, g_trans, g_focal, g_scale, None, None, None, None, None, None)
 
 
 class PoseFn(torch.autograd.Function):

@@ -10,7 +10,10 @@ import torch
 
 from . import _lib, ops
 
-_options = {"voxels": True, "drc_probs": True, "deterministic": False}
+# plane_local: build/gather every Z-plane in shared memory (default); False keeps
+# the raw grid in global memory (memset + atomic scatter, grid gather) -- same
+# results to rounding, kept for A/B measurements
+_options = {"voxels": True, "drc_probs": True, "deterministic": False, "plane_local": True}
 
 
 def set_outputs(voxels=None, drc_probs=None):
@@ -135,7 +138,7 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation, 
     params = ops.make_params(cfg, P, N, flip_y=True)
     mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
         pts, quat, trans, focal, scale, params, ops.host_taps(kernel),
-        _options["voxels"], _options["drc_probs"], _scatter_mode())
+        _options["voxels"], _options["drc_probs"], _scatter_mode(), _options["plane_local"])
     return {
         "proj": mask.unsqueeze(-1),
         "voxels": None if voxels is None else voxels.unsqueeze(-1),

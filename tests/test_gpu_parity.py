@@ -189,3 +189,25 @@ def test_upstream_grads_on_every_output(dpc):
     gc = torch.autograd.grad(loss_of(c, dev), list(leaves_c.values()))
     for k, a, b in zip(leaves_o, gc, go):
         assert _golden.rel_err(a, b) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("V,N,sigma,kind", [(64, 8000, 3.0, "uniform"), (32, 1500, 0.7, "clustered"),
+                                            (128, 4000, 3.0, "uniform")])
+def test_plane_local_path_matches_global_grid_path(dpc, V, N, sigma, kind):
+    """The default path (planes built / gathered in shared memory) against the
+    path that keeps the raw grid in global memory: same math, different
+    association of the fp32 sums -> agreement to rounding, on every output
+    and gradient, including a degenerate cloud that piles into few cells."""
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=21 if V > 32 else 11)
+    case = _inputs.make_case(cfg, 3, N, 77 + V, kind=kind, translation=True, focal=True,
+                             screened=False)
+    case["points"][2, : N // 2] = case["points"][2, 0]          # N/2 points in ONE cell
+    case["kernel"] = CF.smoothing_taps(cfg, sigma)
+    out_p, loss_p, grads_p = run_cuda(dpc, cfg, case, 3, V)
+    with dpc.options(plane_local=False):
+        out_g, loss_g, grads_g = run_cuda(dpc, cfg, case, 3, V)
+    for k in ("proj", "proj_depth", "voxels", "drc_probs"):
+        assert _golden.rel_err(out_p[k], out_g[k]) < FWD_TOL, k
+    assert torch.equal(out_p["tr_pc"], out_g["tr_pc"])
+    for k in grads_p:
+        assert _golden.rel_err(grads_p[k], grads_g[k]) < GRAD_TOL, k
