@@ -50,6 +50,7 @@ WORKLOADS = {
               P=128, N=16000, V=128, K=21, sigma=3.0),
 }
 N_INPUT_SETS = 3          # distinct input sets rotated between steps
+E2E_GRAPH_STEPS = 12      # e2e steps captured per CUDA graph (a multiple of N_INPUT_SETS)
 
 
 def algorithmic_bytes(N, V, Vz):
@@ -263,7 +264,9 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, join=()):
+        """CUDA events on the launching stream over exactly `steps` steps; `join` = side
+        streams whose work (the last step's copies) must be inside the timed region."""
         for i in range(warmup):
             fn(i)
         fence()
@@ -271,6 +274,8 @@ def run_b200(args, rank, world, local_rank):
         e0.record(stream)
         for i in range(steps):
             fn(warmup + i)
+        for side in join:
+            stream.wait_stream(side)
         e1.record(stream)
         fence()
         ms = e0.elapsed_time(e1)
@@ -330,23 +335,42 @@ def run_b200(args, rank, world, local_rank):
     h2d = sum(host[0][k].numel() * 4 for k in ("points", "quat", "scale"))
     d2h = sum(v.numel() * 4 for v in out_host.values())
 
+    pipe = dpc.HostPipeline(dev, depth=3)
+
     def step_e2e(i):
+        # this step's inputs: pinned host memory -> device (copy stream, overlapped with the
+        # previous step's kernels); results and gradients: device -> pinned host memory
+        # (readback stream, overlapped with the next step's kernels)
         h = host[i % N_INPUT_SETS]
-        pts = h["points"].to(dev, non_blocking=True).requires_grad_()
-        quat = h["quat"].to(dev, non_blocking=True).requires_grad_()
-        scale = h["scale"].to(dev, non_blocking=True).requires_grad_()
+        din = pipe.upload({"points": h["points"], "quat": h["quat"], "scale": h["scale"]})
+        pts = din["points"].detach().requires_grad_()
+        quat = din["quat"].detach().requires_grad_()
+        scale = din["scale"].detach().requires_grad_()
         d = devin[i % N_INPUT_SETS]
         out = dpc.pointcloud_project_fast(cfg, pts, quat, None, None, kern, scaling_factor=scale)
         gp, gq, gs = torch.autograd.grad([out["proj"], out["proj_depth"]], [pts, quat, scale],
                                          [d["g_mask"], d["g_depth"]])
-        out_host["mask"].copy_(out["proj"].detach(), non_blocking=True)
-        out_host["depth"].copy_(out["proj_depth"].detach(), non_blocking=True)
-        out_host["g_points"].copy_(gp, non_blocking=True)
-        out_host["g_quat"].copy_(gq, non_blocking=True)
-        out_host["g_scale"].copy_(gs, non_blocking=True)
+        pipe.download({"mask": out["proj"], "depth": out["proj_depth"], "g_points": gp,
+                       "g_quat": gq, "g_scale": gs}, out_host)
+        assert pipe.h2d_bytes == h2d and pipe.d2h_bytes == d2h
 
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    e2e_mode = "eager"
+    if args.graph:
+        # E2E_GRAPH_STEPS consecutive e2e steps (each with its own H2D and D2H copies) captured
+        # once with the public GraphedSteps helper and replayed: the eager loop is bound by
+        # the host (~0.35 ms of Python / autograd-engine work per ~0.2 ms step)
+        gs = dpc.GraphedSteps(step_e2e, E2E_GRAPH_STEPS, dev, pipe=pipe, warmup=2)
+        reps = (args.steps + E2E_GRAPH_STEPS - 1) // E2E_GRAPH_STEPS
 
+        def replay_e2e(i):
+            if i % E2E_GRAPH_STEPS == 0:
+                gs.replay()
+        ms_e2e = timed(replay_e2e, reps * E2E_GRAPH_STEPS, 2 * E2E_GRAPH_STEPS) * args.steps / (
+            reps * E2E_GRAPH_STEPS)
+        e2e_mode = "GraphedSteps(%d steps per CUDA graph)" % E2E_GRAPH_STEPS
+    else:
+        ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), join=(pipe.h2d, pipe.d2h))
+    pipe.drain()
     # ---- (3) per-stage CUDA-event timings for the roofline ----
     stage_ms = (ctypes.c_float * len(_lib.PROFILE_STAGES))()
     d = devin[0]
@@ -399,7 +423,10 @@ def run_b200(args, rank, world, local_rank):
                    "parallelism": "projections sharded across ranks, no collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                "api": "pytorch_unsup_pc_b200.pointcloud_project_fast + torch.autograd.grad"},
+                "api": "pytorch_unsup_pc_b200.pointcloud_project_fast + torch.autograd.grad, "
+                       "host copies through pytorch_unsup_pc_b200.HostPipeline (3 streams: this "
+                       "step's H2D / kernels / D2H overlap the neighbouring steps')",
+                "mode": e2e_mode},
         "gpu_launches": 6 * args.steps,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None,

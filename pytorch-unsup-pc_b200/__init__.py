@@ -11,12 +11,13 @@ from .point_cloud import (pc_perspective_transform, pointcloud2voxels3d_fast,
                           pointcloud_project_fast, smoothen_voxels3d, set_outputs,
                           set_deterministic, options)
 from .drc import drc_depth_projection, drc_event_probabilities, drc_projection
+from .pipeline import GraphedSteps, HostPipeline
 
 __all__ = [
     "pointcloud_project_fast", "pc_perspective_transform", "pointcloud2voxels3d_fast",
     "smoothen_voxels3d", "drc_projection", "drc_depth_projection", "drc_event_probabilities",
     "smoothing_kernel", "gauss_kernel_1d", "separable_kernels",
-    "set_outputs", "set_deterministic", "options", "library_path", "version",
+    "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "library_path", "version",
 ]
 
 

@@ -19,7 +19,26 @@ def _ptr(t):
 
 
 def _stream(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    # the raw handle of torch's current stream (torch.cuda.current_stream() builds a
+    # Python Stream object every call: ~10 us, which matters at ~200 us per step)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(device.index))
+
+
+class _on_device:
+    """``with torch.cuda.device(dev)`` only when ``dev`` is not already current."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if torch._C._cuda_getDevice() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _f32(t, name, shape=None):
@@ -64,7 +83,10 @@ def host_taps(kernel):
         raise ValueError("kernel must be the [X, Y, Z] list smoothing_kernel returns")
     out = []
     for k in kernel:
-        k = torch.as_tensor(k).detach().reshape(-1).to(device="cpu", dtype=torch.float32)
+        if not (isinstance(k, torch.Tensor) and k.dtype == torch.float32 and not k.is_cuda
+                and not k.requires_grad and k.is_contiguous()):
+            k = torch.as_tensor(k).detach().to(device="cpu", dtype=torch.float32)
+        k = k.reshape(-1)
         if k.numel() % 2 == 0 or k.numel() > _lib.MAX_TAPS:
             raise ValueError("Gaussian kernel size %d must be odd and <= %d"
                              % (k.numel(), _lib.MAX_TAPS))
@@ -84,12 +106,18 @@ def _tap_args(taps):
 def _workspace(params, device):
     """One cached workspace per (device, size class); stream-ordered reuse."""
     need = _lib.load().dpc_workspace_bytes(ctypes.byref(params))
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
-    return ws
+    return _scratch("ws", need, device)
+
+
+def _scratch(kind, nbytes, device):
+    """Cached scratch bytes per (kind, device, stream): contents are dead between
+    calls and every use is ordered on that stream, so reuse needs no allocation."""
+    key = (kind, device.index, torch._C._cuda_getCurrentRawStream(device.index))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
 
 
 class ProjectFn(torch.autograd.Function):
@@ -112,34 +140,42 @@ class ProjectFn(torch.autograd.Function):
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
         f32 = dict(dtype=torch.float32, device=dev)
         tr_pc = torch.empty(P, N, 3, **f32)
-        grid_b = torch.empty(P, Vz, V, V, **f32)
-        bits = torch.empty(P, Vz, V, V // 32, dtype=torch.int32, device=dev)
         mask = torch.empty(P, V, V, **f32)
         depth = torch.empty(P, V, V, **f32)
         voxels = torch.empty(P, Vz, V, V, **f32) if want_voxels else None
         probs = torch.empty(Vz + 1, P, V, V, **f32) if want_probs else None
-        # per-point cell records: the plane-local scatter/gather path (default mode)
-        cells = None
-        if int(mode) == _lib.SCATTER_ATOMIC and plane_local:
-            cells = torch.empty(lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8,
-                                device=dev)
+        # state saved for the backward, ONE allocation: blurred grid | clamp bits | per-point
+        # cell records (plane-local scatter/gather path, the default mode)
+        use_cells = int(mode) == _lib.SCATTER_ATOMIC and plane_local
+        n_grid = P * Vz * V * V * 4
+        n_bits = P * Vz * V * (V // 32) * 4
+        n_cells = lib.dpc_cells_bytes(ctypes.byref(params)) if use_cells else 0
+        state = torch.empty(n_grid + n_bits + n_cells, dtype=torch.uint8, device=dev)
+        base = state.data_ptr()
+        grid_b, bits = ctypes.c_void_p(base), ctypes.c_void_p(base + n_grid)
+        cells = ctypes.c_void_p(base + n_grid + n_bits) if use_cells else None
         ws = _workspace(params, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_project_fwd(
                 ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
-                _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), _ptr(grid_b), _ptr(bits),
-                _ptr(cells), _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws),
+                _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), grid_b, bits,
+                cells, _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws),
                 ws.numel(), _stream(dev))
         _lib.check(st, "project_fwd")
-        ctx.save_for_backward(points, quat, trans, focal, scale, grid_b, bits, cells)
+        ctx.save_for_backward(points, quat, trans, focal, scale, state)
         ctx.params, ctx.taps = params, taps
+        ctx.state_layout = (n_grid, n_bits, use_cells)
         ctx.set_materialize_grads(False)
         return mask, depth, tr_pc, voxels, probs
 
     @staticmethod
     def backward(ctx, g_mask, g_depth, g_trpc, g_voxels, g_probs):
         lib = _lib.load()
-        points, quat, trans, focal, scale, grid_b, bits, cells = ctx.saved_tensors
+        points, quat, trans, focal, scale, state = ctx.saved_tensors
+        n_grid, n_bits, use_cells = ctx.state_layout
+        base = state.data_ptr()
+        grid_b, bits = ctypes.c_void_p(base), ctypes.c_void_p(base + n_grid)
+        cells = ctypes.c_void_p(base + n_grid + n_bits) if use_cells else None
         params = ctx.params
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
@@ -149,17 +185,17 @@ class ProjectFn(torch.autograd.Function):
         g_trpc = _f32(g_trpc, "g_tr_pc", (P, N, 3))
         g_voxels = _f32(g_voxels, "g_voxels", (P, Vz, V, V))
         g_probs = _f32(g_probs, "g_probs", (Vz + 1, P, V, V))
-        g_grid = torch.empty(P, Vz, V, V, **f32)
+        g_grid = _scratch("g_grid", n_grid, dev)      # dead after this call
         g_points = torch.empty(P, N, 3, **f32)
         g_quat = torch.empty(P, 4, **f32)
         g_trans = torch.empty(P, 3, **f32) if trans is not None else None
         g_focal = torch.empty(P, **f32) if focal is not None else None
         g_scale = torch.empty(P, **f32) if scale is not None else None
         ws = _workspace(params, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_project_bwd(
                 ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
-                _ptr(scale), *_tap_args(ctx.taps), _ptr(grid_b), _ptr(bits), _ptr(cells),
+                _ptr(scale), *_tap_args(ctx.taps), grid_b, bits, cells,
                 _ptr(g_mask), _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid),
                 _ptr(g_points), _ptr(g_quat), _ptr(g_trans), _ptr(g_focal), _ptr(g_scale),
                 _ptr(ws), ws.numel(), _stream(dev))
@@ -175,7 +211,7 @@ class PoseFn(torch.autograd.Function):
         lib = _lib.load()
         dev = points.device
         tr_pc = torch.empty(params.P, params.N, 3, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_pose_fwd(ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans),
                                   _ptr(focal), _ptr(tr_pc), _stream(dev))
         _lib.check(st, "pose_fwd")
@@ -196,7 +232,7 @@ class PoseFn(torch.autograd.Function):
         g_trans = torch.empty(params.P, 3, **f32) if trans is not None else None
         g_focal = torch.empty(params.P, **f32) if focal is not None else None
         ws = _workspace(params, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_pose_bwd(ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans),
                                   _ptr(focal), _ptr(g_trpc), _ptr(g_points), _ptr(g_quat),
                                   _ptr(g_trans), _ptr(g_focal), _ptr(ws), ws.numel(), _stream(dev))
@@ -213,7 +249,7 @@ class ScatterFn(torch.autograd.Function):
         dev = tr_pc.device
         grid = torch.empty(params.P, params.Vz, params.V, params.V, dtype=torch.float32, device=dev)
         ws = _workspace(params, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_scatter_fwd(ctypes.byref(params), _ptr(tr_pc), _ptr(grid), int(mode),
                                      _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(st, "scatter_fwd")
@@ -229,7 +265,7 @@ class ScatterFn(torch.autograd.Function):
         dev = tr_pc.device
         g_grid = _f32(g_grid, "g_grid", (params.P, params.Vz, params.V, params.V))
         g_trpc = torch.empty_like(tr_pc)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_scatter_bwd(ctypes.byref(params), _ptr(tr_pc), _ptr(g_grid), _ptr(g_trpc),
                                      _stream(dev))
         _lib.check(st, "scatter_bwd")
@@ -240,7 +276,7 @@ def _blur3d(x, params, taps):
     lib = _lib.load()
     dev = x.device
     out = torch.empty_like(x)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         st = lib.dpc_blur3d(ctypes.byref(params), _ptr(x), _ptr(out), *_tap_args(taps),
                             _stream(dev))
     _lib.check(st, "blur3d")
@@ -278,7 +314,7 @@ class DrcFn(torch.autograd.Function):
         mask = torch.empty(P, V, V, **f32)
         depth = torch.empty(P, V, V, **f32)
         probs = torch.empty(Vz + 1, P, V, V, **f32)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_drc_fwd(ctypes.byref(params), _ptr(vox), _ptr(mask), _ptr(depth),
                                  _ptr(probs), _stream(dev))
         _lib.check(st, "drc_fwd")
@@ -299,7 +335,7 @@ class DrcFn(torch.autograd.Function):
         g_probs = _f32(g_probs, "g_probs", (Vz + 1, P, V, V))
         g_vox = torch.empty_like(vox)
         ws = _workspace(params, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_drc_bwd(ctypes.byref(params), _ptr(vox), _ptr(g_mask), _ptr(g_depth),
                                  _ptr(g_probs), _ptr(g_vox), _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(st, "drc_bwd")
@@ -314,7 +350,7 @@ class DepthFromProbsFn(torch.autograd.Function):
         lib = _lib.load()
         dev = probs.device
         depth = torch.empty(params.P, params.V, params.V, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_depth_from_probs_fwd(ctypes.byref(params), _ptr(probs), _ptr(depth),
                                               _stream(dev))
         _lib.check(st, "depth_from_probs_fwd")
@@ -329,7 +365,7 @@ class DepthFromProbsFn(torch.autograd.Function):
         g_depth = _f32(g_depth, "g_depth", (params.P, params.V, params.V))
         g_probs = torch.empty(params.Vz + 1, params.P, params.V, params.V, dtype=torch.float32,
                               device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = lib.dpc_depth_from_probs_bwd(ctypes.byref(params), _ptr(g_depth), _ptr(g_probs),
                                               _stream(dev))
         _lib.check(st, "depth_from_probs_bwd")
