@@ -237,8 +237,8 @@ def run_b200(args, rank, world, local_rank):
                mask=torch.empty(P, V, V, **f32), depth=torch.empty(P, V, V, **f32),
                g_grid=torch.empty(P, Vz, V, V, **f32), g_points=torch.empty(P, N, 3, **f32),
                g_quat=torch.empty(P, 4, **f32), g_scale=torch.empty(P, **f32),
-               cells=torch.empty(lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8,
-                                 device=dev))
+               cells=None if args.global_grid else torch.empty(
+                   lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev))
     ws = torch.empty(lib.dpc_workspace_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sptr = ctypes.c_void_p(stream.cuda_stream)
@@ -329,6 +329,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- (2) e2e: public Python API, pinned host inputs in, results out, every step ----
     dpc.set_outputs(voxels=False, drc_probs=False)
+    dpc.point_cloud._options["plane_local"] = not args.global_grid
     out_host = dict(mask=torch.empty(P, V, V, 1).pin_memory(), depth=torch.empty(P, V, V, 1).pin_memory(),
                     g_points=torch.empty(P, N, 3).pin_memory(), g_quat=torch.empty(P, 4).pin_memory(),
                     g_scale=torch.empty(P, 1).pin_memory())
@@ -416,7 +417,8 @@ def run_b200(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": w["name"], "P_per_gpu": P, "N": N, "V": V, "Vz": Vz, "K": w["K"],
-                   "sigma": w["sigma"], "scatter": "atomic",
+                   "sigma": w["sigma"],
+                   "scatter": "global grid, atomic" if args.global_grid else "plane-local (shared memory)",
                    "l2": "no flush: %d input sets rotate and each step's grid + gradient-grid "
                          "working set (%d MiB) exceeds the 126 MB L2" % (
                              N_INPUT_SETS, 2 * P * Vz * V * V * 4 >> 20),
@@ -427,7 +429,7 @@ def run_b200(args, rank, world, local_rank):
                        "host copies through pytorch_unsup_pc_b200.HostPipeline (3 streams: this "
                        "step's H2D / kernels / D2H overlap the neighbouring steps')",
                 "mode": e2e_mode},
-        "gpu_launches": 6 * args.steps,
+        "gpu_launches": (6 if args.global_grid else 7) * args.steps,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src,
@@ -449,6 +451,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-grid", action="store_true",
+                    help="A/B: keep the raw grid in global memory (memset + atomic scatter, grid "
+                         "gather) instead of the default plane-local path")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue the C-ABI calls from the host every step instead of replaying "
                          "them from a CUDA graph")

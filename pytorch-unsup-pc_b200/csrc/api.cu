@@ -305,12 +305,17 @@ struct FwdPtrs {
   void *cells;
 };
 
+// The plane-local path packs (n, iy, ix) into 32 bits and bins by a z-cell byte.
+static bool plane_local_ok(const dpc_params *p) {
+  return p->N <= 65535 && p->V <= 256 && p->Vz <= 192;
+}
+
 // the records of projections [b0, b0 + n) inside a whole-batch cells buffer
 static CellsView cells_range(void *base, const dpc_params *p, int b0) {
   CellsView v = cells_view(base, p->P, p->N, p->Vz);
   v.cellz += (size_t)b0 * v.Npad;
   v.rec += (size_t)b0 * p->N;
-  v.order += (size_t)b0 * p->N;
+  v.srec += (size_t)b0 * p->N;
   v.binstart += (size_t)b0 * v.zstride;
   return v;
 }
@@ -373,6 +378,7 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
   DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
   DPC_REQUIRE(mask);
   if (scatter_mode == DPC_SCATTER_SORTED) cells = nullptr;   // the sorted scatter builds the grid itself
+  if (!plane_local_ok(p)) cells = nullptr;
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
   DPC_TRY(check_taps(tz, kz, "taps_z"));
   if (scatter_mode != DPC_SCATTER_SORTED && scatter_mode != DPC_SCATTER_ATOMIC) {
@@ -489,6 +495,7 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   DPC_TRY(check_ws(p, workspace, workspace_bytes));
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!plane_local_ok(p)) cells = nullptr;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
                   g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
                   const_cast<void *>(cells)};

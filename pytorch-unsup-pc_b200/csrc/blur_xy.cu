@@ -81,14 +81,20 @@ struct XYCfg {
 };
 
 // 16 packed outputs from a window of W pair-positions starting at `win`
-template <int R, int J, int W2>
+template <int R, int J, int W2, bool MIN1 = false>
 __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, const u64 (&k2)[2 * R + 1],
                                             u64 (&acc)[J]) {
 #pragma unroll
   for (int j = 0; j < J; ++j) acc[j] = 0;
 #pragma unroll
   for (int i = 0; i < W2; ++i) {
-    const float4 v4 = *reinterpret_cast<const float4 *>(win + 2 * i);
+    float4 v4 = *reinterpret_cast<const float4 *>(win + 2 * i);
+    if (MIN1) {   // clamp(raw, 0, 1) of a non-negative raw value, taken on the way in
+      v4.x = fminf(v4.x, 1.f);
+      v4.y = fminf(v4.y, 1.f);
+      v4.z = fminf(v4.z, 1.f);
+      v4.w = fminf(v4.w, 1.f);
+    }
     const u64 vv[2] = {bx_pack2(v4.x, v4.y), bx_pack2(v4.z, v4.w)};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -109,19 +115,33 @@ __device__ __forceinline__ float4 clamp01(float4 v) {
   return v;
 }
 
-// f(n, dz) for every point n of projection b whose trilinear cell touches
+// f(record, dz) for every point of projection b whose trilinear cell touches
 // plane z: dz = 0 when z is the cell's lower plane (iz == z, weight 1 - rz),
-// dz = 1 when it is the upper one (iz == z - 1, weight rz).  The points are
-// binned by z cell (bin_points_kernel), so the ~2N/Vz touching points are ONE
-// contiguous range of the order array: no scan, no compaction, every lane busy.
+// dz = 1 when it is the upper one (iz == z - 1, weight rz).  The records are
+// sorted by z cell (bin_points_kernel), so the ~2N/Vz touching points are ONE
+// contiguous range: coalesced 16-byte loads, no scan, every lane busy.
 template <typename F>
 __device__ __forceinline__ void for_each_touching_point(const CellsView &cells, int b, int z,
                                                         int N, int tid, int nthreads, F &&f) {
   const uint32_t *bs = cells.binstart + (size_t)b * cells.zstride;
   const uint32_t mid = __ldg(bs + z), hi = __ldg(bs + z + 1);
   const uint32_t lo = z > 0 ? __ldg(bs + z - 1) : mid;
-  const uint32_t *order = cells.order + (size_t)b * N;
-  for (uint32_t i = lo + tid; i < hi; i += nthreads) f((int)__ldg(order + i), i < mid ? 1 : 0);
+  const uint4 *srec = cells.srec + (size_t)b * N;
+  for (uint32_t i = lo + tid; i < hi; i += nthreads) f(__ldg(srec + i), i < mid ? 1 : 0);
+}
+
+// Shared-memory float add that returns the NEW value (fp32 shared atomics are a
+// CAS loop in SASS anyway; writing it out gives us the value for free).
+__device__ __forceinline__ float smem_add_new(float *p, float w) {
+  int *ip = reinterpret_cast<int *>(p);
+  int old = *ip, assumed;
+  float nv;
+  do {
+    assumed = old;
+    nv = __int_as_float(assumed) + w;
+    old = atomicCAS(ip, assumed, __float_as_int(nv));
+  } while (old != assumed);
+  return nv;
 }
 
 __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
@@ -163,9 +183,14 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
           reinterpret_cast<float4 *>(A2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
       }
-      for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](int n, int dz) {
-        const uint4 r = __ldg(cells.rec + (size_t)pb * N + n);
-        const int iy = (int)(r.x >> 16), ix = (int)(r.x & 0xFFFFu);
+      // raw <= 1 mask of these rows, one bit per voxel: all ones, and the add that takes
+      // a voxel above 1 clears its bit (weights are >= 0, so a voxel ends above 1 exactly
+      // when its last add produced a value above 1)
+      uint32_t *sbits = reinterpret_cast<uint32_t *>(smem2 + C::TILE_LINES * C::S);
+      for (int i = tid; i < C::RH * V / 32; i += C::THREADS) sbits[i] = 0xffffffffu;
+      __syncthreads();
+      for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](const uint4 r, int dz) {
+        const int iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
         const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
         const float wz = dz ? rz : 1.f - rz;
 #pragma unroll
@@ -174,29 +199,16 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
           if (iy + dy >= V || lr < 0 || lr >= C::RH) continue;
           const float wzy = wz * (dy ? ry : 1.f - ry);
           float *cellp = reinterpret_cast<float *>(A2 + (lr % HALF) * C::S + R + ix) + lr / HALF;
-          atomicAdd(cellp, wzy * (1.f - rx));
-          if (ix + 1 < V) atomicAdd(cellp + 2, wzy * rx);
+          if (smem_add_new(cellp, wzy * (1.f - rx)) > 1.f)
+            atomicAnd(sbits + (lr * V + ix) / 32, ~(1u << (ix & 31)));
+          if (ix + 1 < V && smem_add_new(cellp + 2, wzy * rx) > 1.f)
+            atomicAnd(sbits + (lr * V + ix + 1) / 32, ~(1u << ((ix + 1) & 31)));
         }
       });
       __syncthreads();
-      // clamp(raw, 0, 1) in place + the raw <= 1 bit mask (one ballot = one 32-voxel word)
-      for (int rp = tid >> 5; rp < HALF; rp += C::THREADS / 32) {
-        const int r0 = h * C::RH + rp, r1 = r0 + HALF;
-#pragma unroll
-        for (int q = 0; q < V / 32; ++q) {
-          float2 *e = A2 + rp * C::S + R + 32 * q + (tid & 31);
-          float2 v = *e;
-          const uint32_t b0 = __ballot_sync(0xffffffffu, v.x <= 1.f);
-          const uint32_t b1 = __ballot_sync(0xffffffffu, v.y <= 1.f);
-          v.x = fminf(fmaxf(v.x, 0.f), 1.f);
-          v.y = fminf(fmaxf(v.y, 0.f), 1.f);
-          *e = v;
-          if ((tid & 31) == 0) {
-            bits_out[plane * (V * V / 32) + (r0 * V) / 32 + q] = b0;
-            bits_out[plane * (V * V / 32) + (r1 * V) / 32 + q] = b1;
-          }
-        }
-      }
+      for (int i = tid; i < C::RH * V / 32; i += C::THREADS)
+        bits_out[plane * (V * V / 32) + h * (C::RH * V / 32) + i] = sbits[i];
+      // clamp(raw, 0, 1) happens in the X pass, on the window loads
     }
     // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
     for (int i = tid; i < ((POINTS && WRITE_BITS) ? 0 : C::FILL_ITEMS); i += C::THREADS) {
@@ -236,7 +248,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     for (int task = tid; task < C::XTASKS; task += C::THREADS) {
       const int rp = task % HALF, x0 = (task / HALF) * C::J;
       u64 acc[C::J];
-      window_fma2<R, C::J, C::W2>(A2 + rp * C::S + x0, k2, acc);
+      window_fma2<R, C::J, C::W2, POINTS && WRITE_BITS>(A2 + rp * C::S + x0, k2, acc);
       if (C::ONE_TILE) __syncthreads();   // every window is in registers: the tile can be reused
       // acc[j] = (out[r0][x0+j], out[r1][x0+j]) -> B2[(x0+j)/2][R + row] = (even col, odd col)
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;
@@ -286,9 +298,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   if (GATHER) {
     __syncthreads();
     const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
-    for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](int n, int dz) {
-      const uint4 r = __ldg(cells.rec + (size_t)pb * N + n);
-      const int iy = (int)(r.x >> 16), ix = (int)(r.x & 0xFFFFu);
+    for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](const uint4 r, int dz) {
+      const int n = (int)(r.x >> 16), iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
       const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
       const bool y1 = iy + 1 < V, x1 = ix + 1 < V;   // out-of-range corners carry no gradient
       const float *g0 = G + iy * V + ix;
@@ -313,7 +324,8 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
 #define DPC_LAUNCH_XY(CL, WB, MO, PT)                                                          \
   do {                                                                                         \
     /* the gather tile lives behind the window tiles when it cannot overlay them */            \
-    const size_t smem = C::SMEM + ((PT && MO && C::YTASKS != C::THREADS) ? V * V * 4 : 0);     \
+    const size_t smem = C::SMEM + ((PT && MO && C::YTASKS != C::THREADS) ? V * V * 4 : 0) +    \
+                        ((PT && WB) ? C::RH * V / 8 : 0);                                      \
     static bool attr_done = false;                                                             \
     if (!attr_done) {                                                                          \
       cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT>,                               \

@@ -60,14 +60,16 @@ struct PoseArgs {
 // that a plane's CTA reads the points touching it as one contiguous range.
 //   cellz    [P][Npad] u8  : z cell index (kCellNone = point outside the frustum;
 //                            padding bytes up to Npad, a multiple of 16, are kCellNone)
-//   rec      [P][N] uint4  : {iy << 16 | ix, bits(rz), bits(ry), bits(rx)}
-//   order    [P][N] u32    : point indices sorted by z cell (valid points only)
-//   binstart [P][zstride]  : order[binstart[z] .. binstart[z+1]) = points with iz == z
+//   rec      [P][N] uint4  : {n << 16 | iy << 8 | ix, bits(rz), bits(ry), bits(rx)} in point
+//                            order (written by the pose kernel, input of the binning)
+//   srec     [P][N] uint4  : the same records sorted by z cell (valid points only)
+//   binstart [P][zstride]  : srec[binstart[z] .. binstart[z+1]) = points with iz == z
+// (n in 16 bits, iy / ix in 8: N <= 65535 and V <= 256 on this path)
 constexpr unsigned kCellNone = 255u;
 struct CellsView {
   uint8_t *cellz;
   uint4 *rec;
-  uint32_t *order;
+  uint4 *srec;
   uint32_t *binstart;
   int Npad, zstride;
 };
@@ -75,15 +77,15 @@ inline int cells_npad(int N) { return (N + 15) & ~15; }
 inline int cells_zstride(int Vz) { return (Vz + 1 + 3) & ~3; }
 inline size_t cells_z_bytes(int P, int N) { return ((size_t)P * cells_npad(N) + 255) & ~(size_t)255; }
 inline size_t cells_bytes(int P, int N, int Vz) {
-  return cells_z_bytes(P, N) + (size_t)P * N * (sizeof(uint4) + sizeof(uint32_t)) +
+  return cells_z_bytes(P, N) + (size_t)P * N * 2 * sizeof(uint4) +
          (size_t)P * cells_zstride(Vz) * sizeof(uint32_t);
 }
 inline CellsView cells_view(void *base, int P, int N, int Vz) {
   CellsView v;
   v.cellz = (uint8_t *)base;
   v.rec = (uint4 *)((char *)base + cells_z_bytes(P, N));
-  v.order = (uint32_t *)(v.rec + (size_t)P * N);
-  v.binstart = v.order + (size_t)P * N;
+  v.srec = v.rec + (size_t)P * N;
+  v.binstart = (uint32_t *)(v.srec + (size_t)P * N);
   v.Npad = cells_npad(N);
   v.zstride = cells_zstride(Vz);
   return v;

@@ -17,6 +17,8 @@
 // adjoint in fp64 and block-reduces the per-projection quaternion /
 // translation / focal partial sums into a fixed-order two-stage reduction, so
 // every gradient is deterministic.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "pose.cuh"
 
@@ -104,42 +106,71 @@ pose_cells_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
   cz[n] = (uint8_t)(c.valid ? (unsigned)c.iz : kCellNone);
   if (c.valid)
     cells.rec[(size_t)b * a.N + n] =
-        make_uint4(((unsigned)c.iy << 16) | (unsigned)c.ix, __float_as_uint((float)c.rz),
+        make_uint4(((unsigned)n << 16) | ((unsigned)c.iy << 8) | (unsigned)c.ix,
+                   __float_as_uint((float)c.rz),
                    __float_as_uint((float)c.ry), __float_as_uint((float)c.rx));
 }
 
-// Counting sort of one projection's points by z cell (one CTA per projection):
-// shared-memory histogram of the z-cell bytes, exclusive scan, placement with
-// shared-memory cursors.  The order inside a bin is arbitrary (the consumers
-// accumulate with atomics or write per-point results), the bins are exact.
-constexpr int kBinThreads = 1024;
+// Counting sort of every projection's point records by z cell, one thread-block
+// CLUSTER of kBinSplit CTAs per projection.  Each CTA histograms ITS quarter of
+// the points in shared memory; after a cluster barrier every CTA reads the
+// other CTAs' histograms through distributed shared memory, which gives it both
+// the per-cell totals (scanned into the cell boundaries) and the number of
+// same-cell points owned by lower-ranked CTAs (its own starting cursor inside
+// each cell); it then places its points' records.  No global atomics, no
+// second kernel, 4x fewer shared-memory atomics per CTA than one CTA per
+// projection.  The order inside a cell is arbitrary (the consumers accumulate
+// with atomics or write per-point results); the cell boundaries are exact.
+constexpr int kBinThreads = 256;
+constexpr int kBinSplit = 4;
 constexpr int kMaxBins = 192;
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __cluster_dims__(kBinSplit, 1, 1) __launch_bounds__(kBinThreads)
 bin_points_kernel(CellsView cells, int N, int Vz) {
-  __shared__ unsigned hist[kMaxBins + 1];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const uint4 *cz = reinterpret_cast<const uint4 *>(cells.cellz + (size_t)b * cells.Npad);
-  uint32_t *order = cells.order + (size_t)b * N;
-  for (int i = tid; i <= Vz; i += kBinThreads) hist[i] = 0;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ unsigned hist[kMaxBins];      // this CTA's counts, read by the whole cluster
+  __shared__ unsigned cursor[kMaxBins + 1];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const unsigned rank = cluster.block_rank();
+  const int n8 = cells.Npad / 8;                          // 8-byte groups of z-cell bytes
+  const int per = (n8 + kBinSplit - 1) / kBinSplit;
+  const int i_lo = rank * per, i_hi = min(n8, i_lo + per);
+  const uint2 *cz = reinterpret_cast<const uint2 *>(cells.cellz + (size_t)b * cells.Npad);
+  const uint4 *rec = cells.rec + (size_t)b * N;
+  uint4 *srec = cells.srec + (size_t)b * N;
+  for (int i = tid; i < kMaxBins; i += kBinThreads) hist[i] = 0;
   __syncthreads();
-  for (int i = tid; i < cells.Npad / 16; i += kBinThreads) {
-    const uint4 w = __ldg(cz + i);
-    const unsigned words[4] = {w.x, w.y, w.z, w.w};
+  for (int i = i_lo + tid; i < i_hi; i += kBinThreads) {
+    const uint2 w = __ldg(cz + i);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const unsigned c = (words[k / 4] >> (8 * (k % 4))) & 0xFFu;
+    for (int k = 0; k < 8; ++k) {
+      const unsigned c = ((k < 4 ? w.x : w.y) >> (8 * (k % 4))) & 0xFFu;
       if (c != kCellNone) atomicAdd(&hist[c], 1u);
     }
   }
-  __syncthreads();
+  cluster.sync();
+  // cell totals and this CTA's offset inside every cell, from the cluster's histograms
+  for (int z = tid; z < kMaxBins; z += kBinThreads) {
+    unsigned total = 0, before = 0;
+    if (z < Vz) {
+#pragma unroll
+      for (unsigned r = 0; r < kBinSplit; ++r) {
+        const unsigned v = *cluster.map_shared_rank(&hist[z], r);
+        total += v;
+        before += r < rank ? v : 0u;
+      }
+    }
+    cursor[z] = total;          // scanned below
+    hist[z] = before;           // own counts are no longer needed locally ...
+  }
+  cluster.sync();               // ... nor remotely: every CTA has read every histogram
   if (tid < 32) {
-    // exclusive scan of Vz (<= 192) counts by one warp, 7 bins per lane
-    constexpr int PER = (kMaxBins + 1 + 31) / 32;   // covers z == Vz, the total
+    // exclusive scan of the <= 192 totals by one warp, 6 cells per lane
+    constexpr int PER = kMaxBins / 32;
     unsigned v[PER], sum = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-      const int z = tid * PER + k;
-      v[k] = z < Vz ? hist[z] : 0u;
+      v[k] = cursor[tid * PER + k];
       sum += v[k];
     }
     unsigned incl = sum;
@@ -149,24 +180,23 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
       if (tid >= o) incl += t;
     }
     unsigned run = incl - sum;
+    uint32_t *bs = cells.binstart + (size_t)b * cells.zstride;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const int z = tid * PER + k;
-      if (z <= Vz) {
-        hist[z] = run;                                        // becomes the bin cursor
-        cells.binstart[(size_t)b * cells.zstride + z] = run;  // z == Vz: the total
-      }
+      if (rank == 0 && z <= Vz) bs[z] = run;              // z == Vz: the total
+      cursor[z] = run + hist[z];
       run += v[k];
     }
+    if (rank == 0 && tid == 31 && Vz == kMaxBins) bs[Vz] = run;
   }
   __syncthreads();
-  for (int i = tid; i < cells.Npad / 16; i += kBinThreads) {
-    const uint4 w = __ldg(cz + i);
-    const unsigned words[4] = {w.x, w.y, w.z, w.w};
+  for (int i = i_lo + tid; i < i_hi; i += kBinThreads) {
+    const uint2 w = __ldg(cz + i);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const unsigned c = (words[k / 4] >> (8 * (k % 4))) & 0xFFu;
-      if (c != kCellNone) order[atomicAdd(&hist[c], 1u)] = (uint32_t)(16 * i + k);
+    for (int k = 0; k < 8; ++k) {
+      const unsigned c = ((k < 4 ? w.x : w.y) >> (8 * (k % 4))) & 0xFFu;
+      if (c != kCellNone) srec[atomicAdd(&cursor[c], 1u)] = __ldg(rec + 8 * i + k);
     }
   }
 }
@@ -464,12 +494,16 @@ int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const fl
 
 int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, cudaStream_t s) {
   dim3 g((cells.Npad + kPoseThreads - 1) / kPoseThreads, a.P), t(kPoseThreads);
-  if (a.Vz > kMaxBins) { set_error("pose_cells: vox_size_z %d > %d", a.Vz, kMaxBins); return DPC_ERR_ARG; }
+  if (a.Vz > kMaxBins || a.N > 65535 || a.V > 256) {
+    set_error("pose_cells: the plane-local path needs vox_size_z <= %d, N <= 65535, vox_size <= 256",
+              kMaxBins);
+    return DPC_ERR_ARG;
+  }
   if (tr_pc)
     pose_cells_kernel<true><<<g, t, 0, s>>>(a, tr_pc, cells);
   else
     pose_cells_kernel<false><<<g, t, 0, s>>>(a, tr_pc, cells);
-  bin_points_kernel<<<a.P, kBinThreads, 0, s>>>(cells, a.N, a.Vz);
+  bin_points_kernel<<<dim3(kBinSplit, a.P), kBinThreads, 0, s>>>(cells, a.N, a.Vz);
   return check_launch("pose_cells");
 }
 
