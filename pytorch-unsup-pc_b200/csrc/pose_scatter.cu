@@ -26,7 +26,13 @@ namespace dpc {
 
 constexpr int kPoseThreads = 256;
 
-int pose_partial_blocks(int N) { return (N + kPoseThreads - 1) / kPoseThreads; }
+// 1-point-per-thread kernels (forward pose / scatter / stand-alone gather)
+static int point_blocks(int N) { return (N + kPoseThreads - 1) / kPoseThreads; }
+// the pose adjoint: kBwdThreads threads x kBwdPts points each per CTA, one row of
+// 8 fp64 partial sums per CTA
+constexpr int kBwdThreads = 128;
+constexpr int kBwdPts = 4;
+int pose_partial_blocks(int N) { return (N + kBwdThreads * kBwdPts - 1) / (kBwdThreads * kBwdPts); }
 
 template <bool WRITE_TRPC, bool SCATTER>
 __global__ void __launch_bounds__(kPoseThreads)
@@ -329,14 +335,41 @@ __global__ void finalize_kernel(PoseArgs a, FinalizeArgs f) {
   finalize_projection(a, f, blockIdx.x, threadIdx.x);
 }
 
+// Sum of 8 per-lane fp64 values over the warp with 9 exchanges instead of 40: a
+// butterfly that HALVES the number of live values at each of the first three
+// steps (lanes whose bit is clear keep the lower half of the values, the others
+// the upper half), then two plain steps on the one value left.  Lane L ends up
+// with the warp total of value ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1); the
+// combination order is fixed, so the result is reproducible.
+__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane) {
+  double a[4];
+  const bool h4 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  double c[2];
+  const bool h3 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h3 ? a[i] : a[i + 2], keep = h3 ? a[i + 2] : a[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const bool h2 = lane & 4;
+  double r = (h2 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h2 ? c[0] : c[1], 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 // partials[b][block][8] = {dq^_w, dq^_x, dq^_y, dq^_z, dt0, dt1, dt2, df}
-__global__ void __launch_bounds__(kPoseThreads)
+__global__ void __launch_bounds__(kBwdThreads)
 gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
                        const float *__restrict__ g_trpc, float *__restrict__ g_points,
                        double *__restrict__ partials, int *__restrict__ counters, FinalizeArgs fin,
                        CellsView cells, const float4 *__restrict__ part) {
   const int b = blockIdx.y;
-  const int n = blockIdx.x * kPoseThreads + threadIdx.x;
   const Quat q = load_quat(a.quat + 4 * b);
   const bool has_t = a.trans != nullptr;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
@@ -347,30 +380,83 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
   }
   const double f = a.focal ? (double)a.focal[b] : a.focal_const;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (n < a.N) {
+  if (part) {
+    // Plane-local path: the cell comes from the saved records, so nothing here
+    // needs the reference's exact fp64 rounding any more -- the adjoint is smooth
+    // in p', zc and q, and fp32 keeps it ~1e-6 relative (tolerance 1e-4).  B200
+    // issues fp64 at 1/8 of the fp32 rate; in fp64 this kernel was bound by it.
+    const float w = q.w, vx = q.x, vy = q.y, vz = q.z, ff = (float)f, cd = (float)a.cam_dist;
+    const float ww = w * w - (vx * vx + vy * vy + vz * vz);
+    float fa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < kBwdPts; ++it) {
+      const int n = (blockIdx.x * kBwdPts + it) * kBwdThreads + threadIdx.x;
+      if (n >= a.N) continue;
+      const size_t pi = ((size_t)b * a.N + n) * 3;
+      const float p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
+      // p' = q^ (0,p) q^* (+ t), zc = p'0 + camera distance
+      const float aw = -(vx * p0 + vy * p1 + vz * p2);
+      const float ax = w * p0 + vy * p2 - vz * p1;
+      const float ay = w * p1 + vz * p0 - vx * p2;
+      const float az = w * p2 + vx * p1 - vy * p0;
+      const float r0 = -aw * vx + ax * w - ay * vz + az * vy + t0;
+      const float r1 = -aw * vy + ay * w - az * vx + ax * vz + t1;
+      const float r2 = -aw * vz + az * w - ax * vy + ay * vx + t2;
+      // the blur-XY adjoint already gathered the corners plane by plane:
+      // part[0] = plane iz, part[1] = plane iz + 1 (absent when iz + 1 == Vz)
+      // (both partials are loaded unconditionally, next to the z-cell byte, and
+      // SELECTED afterwards: an unwritten slot may hold anything, NaN included)
+      const size_t idx = (size_t)b * a.N + n;
+      const unsigned iz = cells.cellz[(size_t)b * cells.Npad + n];
+      const float4 s0 = __ldg(part + idx), s1 = __ldg(part + (size_t)a.P * a.N + idx);
+      const bool in0 = iz != kCellNone, in1 = in0 && (int)iz + 1 < a.Vz;
+      float gu0 = ((in0 ? s0.x : 0.f) + (in1 ? s1.x : 0.f)) * (float)(a.Vz - 1);
+      float gu1 = ((in0 ? s0.y : 0.f) + (in1 ? s1.y : 0.f)) * (float)(a.V - 1);
+      float gu2 = ((in0 ? s0.z : 0.f) + (in1 ? s1.z : 0.f)) * (float)(a.V - 1);
+      if (g_trpc) {
+        gu0 += g_trpc[pi];
+        gu1 += g_trpc[pi + 1];
+        gu2 += g_trpc[pi + 2];
+      }
+      // perspective adjoint
+      const float izc = 1.f / (r0 + cd);
+      const float s12 = (r1 * gu1 + r2 * gu2) * izc;
+      const float g0 = gu0 - ff * s12 * izc, g1 = ff * gu1 * izc, g2 = ff * gu2 * izc;
+      // rotation adjoint for F(q^) = (w^2-|v|^2) p + 2 (v.p) v + 2 w (v x p)
+      const float vg = vx * g0 + vy * g1 + vz * g2;
+      const float vp = vx * p0 + vy * p1 + vz * p2;
+      const float gp = g0 * p0 + g1 * p1 + g2 * p2;
+      const float c0 = vy * g2 - vz * g1, c1 = vz * g0 - vx * g2, c2 = vx * g1 - vy * g0;   // v x g
+      g_points[pi] = ww * g0 + 2.f * vg * vx - 2.f * w * c0;
+      g_points[pi + 1] = ww * g1 + 2.f * vg * vy - 2.f * w * c1;
+      g_points[pi + 2] = ww * g2 + 2.f * vg * vz - 2.f * w * c2;
+      const float x0 = p1 * g2 - p2 * g1, x1 = p2 * g0 - p0 * g2, x2 = p0 * g1 - p1 * g0;   // p x g
+      fa[0] += 2.f * w * gp + 2.f * (vx * x0 + vy * x1 + vz * x2);
+      fa[1] += -2.f * gp * vx + 2.f * (vg * p0 + vp * g0) + 2.f * w * x0;
+      fa[2] += -2.f * gp * vy + 2.f * (vg * p1 + vp * g1) + 2.f * w * x1;
+      fa[3] += -2.f * gp * vz + 2.f * (vg * p2 + vp * g2) + 2.f * w * x2;
+      fa[4] += g0 - gu0;
+      fa[5] += g1;
+      fa[6] += g2;
+      fa[7] += s12;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (double)fa[i];   // cross-thread sums stay in fp64
+  } else {
+  const double w = q.w, vx = q.x, vy = q.y, vz = q.z;
+  const double ww = w * w - (vx * vx + vy * vy + vz * vz);
+  // kBwdPts points per thread, a CTA-wide stride apart (coalesced); the thread's
+  // partial sums stay in registers, so the reductions below run once per 4 points
+#pragma unroll
+  for (int it = 0; it < kBwdPts; ++it) {
+    const int n = (blockIdx.x * kBwdPts + it) * kBwdThreads + threadIdx.x;
+    if (n >= a.N) continue;
     const size_t pi = ((size_t)b * a.N + n) * 3;
     const double p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
     const PosePoint pp = pose_point(q, (float)p0, (float)p1, (float)p2, has_t, t0, t1, t2, f,
                                     a.cam_dist);
     double gu0 = 0, gu1 = 0, gu2 = 0;
-    if (part) {
-      // the blur-XY adjoint already gathered the corners plane by plane:
-      // part[0] = plane iz, part[1] = plane iz + 1 (absent when iz + 1 == Vz)
-      const unsigned iz = cells.cellz[(size_t)b * cells.Npad + n];
-      if (iz != kCellNone) {
-        const size_t idx = (size_t)b * a.N + n;
-        float4 s0 = __ldg(part + idx);
-        if ((int)iz + 1 < a.Vz) {
-          const float4 s1 = __ldg(part + (size_t)a.P * a.N + idx);
-          s0.x += s1.x;
-          s0.y += s1.y;
-          s0.z += s1.z;
-        }
-        gu0 = (double)s0.x * (double)(a.Vz - 1);
-        gu1 = (double)s0.y * (double)(a.V - 1);
-        gu2 = (double)s0.z * (double)(a.V - 1);
-      }
-    } else if (g_grid) {
+    if (g_grid) {
       const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
       if (c.valid) gather_cell(c, g_grid + (size_t)b * a.Vz * a.V * a.V, a.Vz, a.V, gu0, gu1, gu2);
     }
@@ -386,11 +472,9 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     const double g1 = f * gu1 * izc;
     const double g2 = f * gu2 * izc;
     // rotation adjoint for F(q^) = (w^2-|v|^2) p + 2 (v.p) v + 2 w (v x p)
-    const double w = q.w, vx = q.x, vy = q.y, vz = q.z;
     const double vg = vx * g0 + vy * g1 + vz * g2;
     const double vp = vx * p0 + vy * p1 + vz * p2;
     const double gp = g0 * p0 + g1 * p1 + g2 * p2;
-    const double ww = w * w - (vx * vx + vy * vy + vz * vz);
     // v x g
     const double c0 = vy * g2 - vz * g1, c1 = vz * g0 - vx * g2, c2 = vx * g1 - vy * g0;
     g_points[pi] = (float)(ww * g0 + 2.0 * vg * vx - 2.0 * w * c0);
@@ -398,30 +482,30 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     g_points[pi + 2] = (float)(ww * g2 + 2.0 * vg * vz - 2.0 * w * c2);
     // p x g
     const double x0 = p1 * g2 - p2 * g1, x1 = p2 * g0 - p0 * g2, x2 = p0 * g1 - p1 * g0;
-    acc[0] = 2.0 * w * gp + 2.0 * (vx * x0 + vy * x1 + vz * x2);  // g.(v x p) = v.(p x g)
-    acc[1] = -2.0 * gp * vx + 2.0 * (vg * p0 + vp * g0) + 2.0 * w * x0;
-    acc[2] = -2.0 * gp * vy + 2.0 * (vg * p1 + vp * g1) + 2.0 * w * x1;
-    acc[3] = -2.0 * gp * vz + 2.0 * (vg * p2 + vp * g2) + 2.0 * w * x2;
-    acc[4] = g0 - gu0;  // dL/dt0 = dL/dp'0 - g_u0
-    acc[5] = g1;
-    acc[6] = g2;
-    acc[7] = s12;       // dL/df
+    acc[0] += 2.0 * w * gp + 2.0 * (vx * x0 + vy * x1 + vz * x2);  // g.(v x p) = v.(p x g)
+    acc[1] += -2.0 * gp * vx + 2.0 * (vg * p0 + vp * g0) + 2.0 * w * x0;
+    acc[2] += -2.0 * gp * vy + 2.0 * (vg * p1 + vp * g1) + 2.0 * w * x1;
+    acc[3] += -2.0 * gp * vz + 2.0 * (vg * p2 + vp * g2) + 2.0 * w * x2;
+    acc[4] += g0 - gu0;  // dL/dt0 = dL/dp'0 - g_u0
+    acc[5] += g1;
+    acc[6] += g2;
+    acc[7] += s12;       // dL/df
   }
-  // fixed-order block reduction: warp shuffles, then warps in index order
-  __shared__ double red[kPoseThreads / 32][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    double v = acc[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
   }
+  // fixed-order block reduction: one butterfly per warp, then warps in index order
+  __shared__ double red[kBwdThreads / 32][8];
+  const int lane = threadIdx.x & 31;
+  const double tot = warp_sum8(acc, lane);
+  if ((lane & 3) == 0) red[threadIdx.x >> 5][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
   __syncthreads();
   if (threadIdx.x < 8) {
     double v = 0;
 #pragma unroll
-    for (int wdx = 0; wdx < kPoseThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
+    for (int wdx = 0; wdx < kBwdThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
     partials[((size_t)b * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
+    // publish the row before the arrival counter is bumped; only the writers fence
+    // (a CTA-wide fence also waits for every warp's g_points stores: 25 % of this kernel)
+    if (counters) __threadfence();
   }
   // Fused finalize: the last block of a projection to arrive reduces all of the
   // projection's partials (in block-index order, so the result does not depend
@@ -429,7 +513,6 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
   // backward kernel earlier in the same pass.
   if (counters) {
     __shared__ int is_last;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(counters + b, 1) == (int)gridDim.x - 1);
     __syncthreads();
@@ -442,7 +525,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
 
 // ---- launchers ---------------------------------------------------------------
 int launch_pose_scatter(const PoseArgs &a, float *tr_pc, float *grid, cudaStream_t s) {
-  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  dim3 g(point_blocks(a.N), a.P), t(kPoseThreads);
   if (tr_pc && grid)
     pose_scatter_kernel<true, true><<<g, t, 0, s>>>(a, tr_pc, grid);
   else if (grid)
@@ -454,14 +537,14 @@ int launch_pose_scatter(const PoseArgs &a, float *tr_pc, float *grid, cudaStream
 
 int launch_scatter_trpc(const float *tr_pc, int P, int N, int Vz, int V, float *grid,
                         cudaStream_t s) {
-  dim3 g(pose_partial_blocks(N), P), t(kPoseThreads);
+  dim3 g(point_blocks(N), P), t(kPoseThreads);
   scatter_trpc_kernel<<<g, t, 0, s>>>(tr_pc, N, Vz, V, grid);
   return check_launch("scatter_trpc");
 }
 
 int launch_gather_pose_bwd(const PoseArgs &a, const float *g_grid, const float *g_trpc,
                            float *g_points, double *partials, cudaStream_t s) {
-  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kBwdThreads);
   gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, nullptr,
                                          FinalizeArgs{}, CellsView{nullptr, nullptr, nullptr, nullptr, 0, 0}, nullptr);
   return check_launch("gather_pose_bwd");
@@ -471,7 +554,7 @@ int launch_gather_pose_finalize(const PoseArgs &a, const float *g_grid, const fl
                                 float *g_points, double *partials, int *counters,
                                 const float *scale_partials, int scale_blocks, float *g_quat,
                                 float *g_trans, float *g_focal, float *g_scale, cudaStream_t s) {
-  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kBwdThreads);
   FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
                  g_quat, g_trans, g_focal, g_scale};
   gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, g_grid, g_trpc, g_points, partials, counters, f,
@@ -484,7 +567,7 @@ int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const fl
                              int *counters, const float *scale_partials, int scale_blocks,
                              float *g_quat, float *g_trans, float *g_focal, float *g_scale,
                              cudaStream_t s) {
-  dim3 g(pose_partial_blocks(a.N), a.P), t(kPoseThreads);
+  dim3 g(pose_partial_blocks(a.N), a.P), t(kBwdThreads);
   FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
                  g_quat, g_trans, g_focal, g_scale};
   gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, nullptr, g_trpc, g_points, partials, counters, f,
@@ -509,7 +592,7 @@ int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, c
 
 int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, const float *g_grid,
                            float *g_trpc, cudaStream_t s) {
-  dim3 g(pose_partial_blocks(N), P), t(kPoseThreads);
+  dim3 g(point_blocks(N), P), t(kPoseThreads);
   gather_trpc_bwd_kernel<<<g, t, 0, s>>>(tr_pc, N, Vz, V, g_grid, g_trpc);
   return check_launch("gather_trpc_bwd");
 }
