@@ -495,7 +495,10 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   DPC_TRY(check_ws(p, workspace, workspace_bytes));
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!plane_local_ok(p)) cells = nullptr;
+  // The plane gather pays off while several CTAs share an SM (V <= 64); a 128^2
+  // plane takes the whole SM's shared memory and its gather runs with nothing to
+  // overlap it (measured at workload B: 1269 vs 773 us), so 128^3 gathers from the grid.
+  if (!plane_local_ok(p) || p->V > 64) cells = nullptr;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
                   g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
                   const_cast<void *>(cells)};

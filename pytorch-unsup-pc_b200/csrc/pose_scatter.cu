@@ -135,6 +135,7 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ unsigned hist[kMaxBins];      // this CTA's counts, read by the whole cluster
+  __shared__ unsigned ahead[kMaxBins];     // same-cell points owned by lower-ranked CTAs
   __shared__ unsigned cursor[kMaxBins + 1];
   const int b = blockIdx.y, tid = threadIdx.x;
   const unsigned rank = cluster.block_rank();
@@ -167,9 +168,9 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
       }
     }
     cursor[z] = total;          // scanned below
-    hist[z] = before;           // own counts are no longer needed locally ...
+    ahead[z] = before;          // (hist itself stays untouched: other CTAs are still reading it)
   }
-  cluster.sync();               // ... nor remotely: every CTA has read every histogram
+  cluster.sync();               // no CTA may exit while its histogram can still be read
   if (tid < 32) {
     // exclusive scan of the <= 192 totals by one warp, 6 cells per lane
     constexpr int PER = kMaxBins / 32;
@@ -191,7 +192,7 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
     for (int k = 0; k < PER; ++k) {
       const int z = tid * PER + k;
       if (rank == 0 && z <= Vz) bs[z] = run;              // z == Vz: the total
-      cursor[z] = run + hist[z];
+      cursor[z] = run + ahead[z];
       run += v[k];
     }
     if (rank == 0 && tid == 31 && Vz == kMaxBins) bs[Vz] = run;
