@@ -68,6 +68,16 @@ def stage_algorithmic_bytes(N, V, Vz):
             "blur_xy_bwd": 5 * G, "gather_pose_bwd": G + 36 * N}
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's kernel at
+# workload A, from the committed `ncu --set full` capture profiles/r01_ncu_full_step_plane_local_v2.csv
+# (cold L2: ncu flushes the caches before every replay).  None = not captured for that workload.
+NCU_TRAFFIC_BYTES = {
+    "A": {"pose_scatter": 6.16e6 + 8.72e6, "blur_xy_fwd": 7.46e6 + 12.07e6,
+          "blurz_drc_fwd": 67.13e6 + 11.02e6, "drc_blurz_bwd": 69.25e6 + 21.03e6,
+          "blur_xy_bwd": 77.09e6 + 3.66e6, "gather_pose_bwd": 23.12e6 + 0.0},
+}
+
+
 def make_cfg(w):
     from oracle.config import default_cfg
     return default_cfg(vox_size=w["V"], pc_gauss_kernel_size=w["K"])
@@ -431,7 +441,11 @@ def run_b200(args, rank, world, local_rank):
                 "mode": e2e_mode},
         "gpu_launches": (6 if args.global_grid else 7) * args.steps,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (None if args.global_grid else
+                                 NCU_TRAFFIC_BYTES.get(args.workload, {}).get(top)),
+                     "traffic_source": "profiles/r01_ncu_full_step_plane_local_v2.csv (ncu --set full, "
+                                       "dram read + write per launch, cold L2)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": sbytes[top] * P,
                      "kernel_ms": stages[top]},

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdpc_b200.so")
+# DPC_B200_LIB: load another build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("DPC_B200_LIB") or os.path.join(_HERE, "lib", "libdpc_b200.so")
 
 c_float_p = ctypes.c_void_p   # device/host pointers travel as raw addresses
 c_void_p = ctypes.c_void_p

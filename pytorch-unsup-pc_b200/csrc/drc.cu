@@ -132,22 +132,30 @@ static RayConst make_ray_const(const DrcArgs &a) {
   return c;
 }
 
+#ifndef DPC_RING_NACC
+#define DPC_RING_NACC 3
+#endif
 // sum_t k[t] * ring[(first + t) % L]  (reversed: k[2R - t]), packed pairs
 template <int R, int L>
 __device__ __forceinline__ u64 ring_dot2(const u64 (&ring)[L], const u64 (&k2)[2 * R + 1],
                                          int first /*compile-time*/, bool reversed) {
   constexpr int W = 2 * R + 1;
-  u64 s0 = 0, s1 = 0, s2 = 0;   // bit pattern 0 == (0.f, 0.f)
+  // NACC independent accumulation chains (fixed association, so reproducible)
+  constexpr int NACC = W >= 12 ? DPC_RING_NACC : (W >= 3 ? 3 : 1);
+  u64 acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0;   // bit pattern 0 == (0.f, 0.f)
 #pragma unroll
   for (int t = 0; t < W; ++t) {
     const u64 v = ring[(first + t) % L];
     const u64 k = reversed ? k2[W - 1 - t] : k2[t];
-    if (t % 3 == 0) s0 = fma2(k, v, s0);
-    else if (t % 3 == 1) s1 = fma2(k, v, s1);
-    else s2 = fma2(k, v, s2);
+    acc[t % NACC] = fma2(k, v, acc[t % NACC]);
   }
-  if (W == 1) return s0;
-  return add2(add2(s0, s1), s2);
+#pragma unroll
+  for (int n = NACC; n > 1; n = (n + 1) / 2)
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) acc[i] = add2(acc[i], acc[n - 1 - i]);
+  return acc[0];
 }
 
 template <int V>
