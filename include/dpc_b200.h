@@ -160,6 +160,33 @@ DPC_API int dpc_project_bwd(const dpc_params *p, const float *points, const floa
                     float *g_focal, float *g_scale,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- f1 (next row): models/model_pc_to.py:339-385 add_proj_loss (candidate
+ * branch) + :410-440 proj_loss_pose_candidates ------------------------------
+ * gt [BV,G,G] ground-truth masks (G a multiple of V: AvgPool2d(G/V) is fused),
+ * pred [BV*C,V,V] candidate masks (candidates of a view adjacent), weights [BV]
+ * valid_samples (NULL ok).  Outputs: all_loss [BV*C] = sum((gt-pred)^2) per
+ * candidate, min_idx [BV] = argmin over the candidates (first minimum),
+ * view_loss [BV] = weights^2 * all_loss[min]; proj_loss = sum(view_loss) / BV. */
+DPC_API int dpc_candidate_loss_fwd(int BV, int C, int V, int G, const float *gt, const float *pred,
+                           const float *weights /*NULL ok*/, float *all_loss, int64_t *min_idx,
+                           float *view_loss, void *stream);
+/* g_pred [BV*C,V,V] = coeff * upstream * d(sum view_loss)/d pred: zero for the
+ * losing candidates.  upstream: device scalar (NULL = 1); coeff: host scalar
+ * (weight_scale / BV). */
+DPC_API int dpc_candidate_loss_bwd(int BV, int C, int V, int G, const float *gt, const float *pred,
+                           const float *weights /*NULL ok*/, const int64_t *min_idx,
+                           const float *upstream /*NULL ok*/, float coeff, float *g_pred,
+                           void *stream);
+
+/* ---- f4 (next row): util/point_cloud_distance.py:25-40 point_cloud_distance
+ * (the kernel of run/eval_chamfer_to.py:24-44 compute_distance) -------------
+ * For every source point src [N,3] the closest target point of tgt [M,3]:
+ * proj [N,3] = that point, min_dist [N] = sqrt of the squared distance,
+ * idx [N] = its index (first minimum, like torch.argmin).  workspace: 8 N bytes. */
+DPC_API int dpc_point_cloud_distance(int N, int M, const float *src, const float *tgt, float *proj,
+                             float *min_dist, int64_t *idx, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* ---- measurement aid (bench.py): runs dpc_project_fwd + dpc_project_bwd
  * `iters` times with a CUDA event recorded on `stream` after every stage and
  * returns the average duration of each stage in milliseconds.  Synchronises

@@ -49,6 +49,12 @@ _DEFAULTS = dict(
     max_depth=10.0,
     max_number_of_steps=600000,
     pc_num_points=8000,
+    # candidate-selection loss, default_config.yaml
+    pose_predict_num_candidates=1,
+    pose_predictor_student=False,
+    variable_num_views=False,
+    pc_gauss_filter_gt=False,
+    proj_weight=1.0,
 )
 
 # experiments/chair_unsupervised/config.yaml:7-14

@@ -124,3 +124,31 @@ def ref_project_literal(cfg, point_cloud, transform, predicted_translation=None,
         return load()["pc_to"].pointcloud_project_fast(
             cfg, point_cloud, transform, predicted_translation, None, kernel,
             scaling_factor=scaling_factor, focal_length=focal_length)
+
+
+def ref_candidate_loss(cfg, masks, projs, weight_scale=1.0, valid_samples=None):
+    """The reference's OWN ``add_proj_loss`` / ``proj_loss_pose_candidates``
+    (models/model_pc_to.py:339-385, 410-440) called unbound on a stub ``self``
+    (the methods only use ``self.cfg()`` and each other)."""
+    load()
+    import models.model_pc_to as model_pc
+
+    class _Stub:
+        def cfg(self_inner):
+            return cfg
+        proj_loss_pose_candidates = model_pc.ModelPointCloud.proj_loss_pose_candidates
+
+    inputs = {"masks": masks}
+    if valid_samples is not None:
+        inputs["valid_samples"] = valid_samples
+    outputs = {"projs": projs}
+    total, min_loss = model_pc.ModelPointCloud.add_proj_loss(_Stub(), inputs, outputs, weight_scale,
+                                                             None, False)
+    return total, min_loss
+
+
+def ref_point_cloud_distance(Vs, Vt):
+    """The reference's own util/point_cloud_distance.py:25-40 on the CPU."""
+    load()
+    import util.point_cloud_distance as pcd
+    return pcd.point_cloud_distance(Vs, Vt)

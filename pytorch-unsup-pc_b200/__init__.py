@@ -12,12 +12,15 @@ from .point_cloud import (pc_perspective_transform, pointcloud2voxels3d_fast,
                           set_deterministic, options)
 from .drc import drc_depth_projection, drc_event_probabilities, drc_projection
 from .pipeline import GraphedSteps, HostPipeline
+from .losses import add_proj_loss, proj_loss_pose_candidates
+from .point_cloud_distance import chamfer_distances, point_cloud_distance
 
 __all__ = [
     "pointcloud_project_fast", "pc_perspective_transform", "pointcloud2voxels3d_fast",
     "smoothen_voxels3d", "drc_projection", "drc_depth_projection", "drc_event_probabilities",
     "smoothing_kernel", "gauss_kernel_1d", "separable_kernels",
-    "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "library_path", "version",
+    "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "add_proj_loss", "proj_loss_pose_candidates", "point_cloud_distance", "chamfer_distances",
+    "library_path", "version",
 ]
 
 

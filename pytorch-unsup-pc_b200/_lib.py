@@ -55,6 +55,9 @@ SIGNATURES = {
                        + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
                        + [c_void_p] * 3 + [c_void_p] * 5 + [c_void_p] * 6
                        + [c_void_p, c_size_t, c_void_p],
+    "dpc_candidate_loss_fwd": [c_int] * 4 + [c_void_p] * 6 + [c_void_p],
+    "dpc_candidate_loss_bwd": [c_int] * 4 + [c_void_p] * 5 + [ctypes.c_float, c_void_p, c_void_p],
+    "dpc_point_cloud_distance": [c_int, c_int] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p],
     "dpc_project_profile": [_P] + [c_void_p] * 5
                            + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
                            + [c_void_p] * 6 + [c_void_p] * 2 + [c_void_p] * 6

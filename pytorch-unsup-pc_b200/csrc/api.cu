@@ -522,6 +522,54 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   return rc;
 }
 
+// ---- f1: candidate-selection projection loss --------------------------------
+static int check_loss_args(int BV, int C, int V, int G) {
+  if (BV < 1 || C < 1 || C > candidate_loss_max_candidates()) {
+    set_error("candidate_loss: BV=%d must be >= 1 and 1 <= num_candidates=%d <= %d", BV, C,
+              candidate_loss_max_candidates());
+    return DPC_ERR_ARG;
+  }
+  if (V < 1 || G < V || G % V != 0) {
+    set_error("candidate_loss: GT size %d must be a multiple of (and not below) the prediction size %d",
+              G, V);
+    return DPC_ERR_ARG;
+  }
+  return DPC_OK;
+}
+
+int dpc_candidate_loss_fwd(int BV, int C, int V, int G, const float *gt, const float *pred,
+                           const float *weights, float *all_loss, int64_t *min_idx,
+                           float *view_loss, void *stream) {
+  DPC_TRY(check_loss_args(BV, C, V, G));
+  DPC_REQUIRE(gt); DPC_REQUIRE(pred); DPC_REQUIRE(all_loss); DPC_REQUIRE(min_idx);
+  DPC_REQUIRE(view_loss);
+  return launch_candidate_loss_fwd(gt, pred, weights, BV, C, V, G, all_loss, (long long *)min_idx,
+                                   view_loss, (cudaStream_t)stream);
+}
+
+int dpc_candidate_loss_bwd(int BV, int C, int V, int G, const float *gt, const float *pred,
+                           const float *weights, const int64_t *min_idx, const float *upstream,
+                           float coeff, float *g_pred, void *stream) {
+  DPC_TRY(check_loss_args(BV, C, V, G));
+  DPC_REQUIRE(gt); DPC_REQUIRE(pred); DPC_REQUIRE(min_idx); DPC_REQUIRE(g_pred);
+  return launch_candidate_loss_bwd(gt, pred, weights, (const long long *)min_idx, upstream, coeff,
+                                   BV, C, V, G, g_pred, (cudaStream_t)stream);
+}
+
+// ---- f4: nearest neighbour of the Chamfer evaluation ---------------------------
+int dpc_point_cloud_distance(int N, int M, const float *src, const float *tgt, float *proj,
+                             float *min_dist, int64_t *idx, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+  if (N < 1 || M < 1) { set_error("point_cloud_distance: N=%d and M=%d must be >= 1", N, M); return DPC_ERR_ARG; }
+  DPC_REQUIRE(src); DPC_REQUIRE(tgt); DPC_REQUIRE(proj); DPC_REQUIRE(min_dist); DPC_REQUIRE(idx);
+  if (!workspace || workspace_bytes < (size_t)N * 8) {
+    set_error("point_cloud_distance: workspace needs %zu bytes, got %zu", (size_t)N * 8, workspace_bytes);
+    return DPC_ERR_WORKSPACE;
+  }
+  return launch_nn_search(src, N, tgt, M, (unsigned long long *)workspace, proj, min_dist,
+                          (long long *)idx, (cudaStream_t)stream);
+}
+
 int dpc_project_profile(const dpc_params *p, const float *points, const float *quat,
                         const float *trans, const float *focal, const float *scale,
                         const float *tx, int kx, const float *ty, int ky, const float *tz, int kz,

@@ -1,0 +1,126 @@
+// Candidate-selection projection loss, fused.
+//
+// Reference: models/model_pc_to.py:339-385 add_proj_loss (AvgPool2d of the
+// ground-truth masks from G x G to the prediction's V x V, :349-356) and
+// :410-440 proj_loss_pose_candidates (per-candidate sum of squared differences,
+// argmin over the candidates, one-hot-masked loss, optional per-sample
+// weights, / BV).  The reference runs this as ~10 ATen launches over P x V x V
+// temporaries (tf_repeat_0 of gt, sq_diff, one_hot, loss_tensor ...).
+//
+// Forward: one CTA per (sample, view) bv.  The pooled ground truth of the view
+// is built once in registers (the G x G mask is read once), each of the C
+// candidate masks is read once, the C sums are block-reduced in fixed order
+// (fp64 across threads), thread 0 takes the first minimum (torch.argmin) and
+// writes the view's weighted loss.  Nothing of size P x V x V is written.
+// Backward: one CTA per (bv, candidate): zeros for the losing candidates,
+// -2 k w^2 (gt - pred) for the winner, with the pooled gt rebuilt on the fly.
+#include "common.cuh"
+
+namespace dpc {
+
+constexpr int kLossThreads = 256;
+constexpr int kMaxCandidates = 16;
+
+// average of the n x n block of gt that pools onto pixel (y, x) (AvgPool2d(n))
+__device__ __forceinline__ float pooled_gt(const float *__restrict__ gt, int G, int n, int y, int x) {
+  if (n == 1) return __ldg(gt + y * G + x);
+  float s = 0.f;
+  for (int dy = 0; dy < n; ++dy) {
+    const float *row = gt + (size_t)(y * n + dy) * G + x * n;
+    if (n == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2 *>(row));
+      s += v.x + v.y;
+    } else {
+      for (int dx = 0; dx < n; ++dx) s += __ldg(row + dx);
+    }
+  }
+  return s / (float)(n * n);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+candidate_loss_fwd_kernel(const float *__restrict__ gt, const float *__restrict__ pred,
+                          const float *__restrict__ weights, int C, int V, int G,
+                          float *__restrict__ all_loss, long long *__restrict__ min_idx,
+                          float *__restrict__ view_loss) {
+  const int bv = blockIdx.x, tid = threadIdx.x, n = G / V, VV = V * V;
+  const float *g = gt + (size_t)bv * G * G;
+  float acc[kMaxCandidates];
+#pragma unroll
+  for (int c = 0; c < kMaxCandidates; ++c) acc[c] = 0.f;
+  for (int i = tid; i < VV; i += kLossThreads) {
+    const int y = i / V, x = i - y * V;
+    const float gp = pooled_gt(g, G, n, y, x);
+#pragma unroll
+    for (int c = 0; c < kMaxCandidates; ++c)
+      if (c < C) {
+        const float d = gp - __ldg(pred + ((size_t)bv * C + c) * VV + i);
+        acc[c] = fmaf(d, d, acc[c]);
+      }
+  }
+  // fixed-order reduction: warp shuffles (fp64), then warps in index order
+  __shared__ double red[kLossThreads / 32][kMaxCandidates];
+#pragma unroll
+  for (int c = 0; c < kMaxCandidates; ++c)
+    if (c < C) {
+      double v = (double)acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) red[tid >> 5][c] = v;
+    }
+  __syncthreads();
+  if (tid == 0) {
+    double best = 0;
+    int arg = 0;
+    for (int c = 0; c < C; ++c) {
+      double v = 0;
+      for (int w = 0; w < kLossThreads / 32; ++w) v += red[w][c];
+      all_loss[(size_t)bv * C + c] = (float)v;
+      if (c == 0 || v < best) { best = v; arg = c; }   // first minimum, like torch.argmin
+    }
+    const double w = weights ? (double)weights[bv] : 1.0;
+    min_idx[bv] = arg;
+    view_loss[bv] = (float)(w * w * best);
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+candidate_loss_bwd_kernel(const float *__restrict__ gt, const float *__restrict__ pred,
+                          const float *__restrict__ weights, const long long *__restrict__ min_idx,
+                          const float *__restrict__ upstream, float coeff, int C, int V, int G,
+                          float *__restrict__ g_pred) {
+  const int img = blockIdx.x, bv = img / C, c = img - bv * C, n = G / V, VV = V * V;
+  float *out = g_pred + (size_t)img * VV;
+  if ((long long)c != min_idx[bv]) {
+    for (int i = threadIdx.x; i < VV; i += kLossThreads) out[i] = 0.f;
+    return;
+  }
+  const float w = weights ? weights[bv] : 1.f;
+  // d/dpred sum(((gt - pred) w)^2) * coeff * upstream = -2 w^2 coeff upstream (gt - pred)
+  const float k = -2.f * w * w * coeff * (upstream ? __ldg(upstream) : 1.f);
+  const float *g = gt + (size_t)bv * G * G;
+  const float *p = pred + (size_t)img * VV;
+  for (int i = threadIdx.x; i < VV; i += kLossThreads) {
+    const int y = i / V, x = i - y * V;
+    out[i] = k * (pooled_gt(g, G, n, y, x) - __ldg(p + i));
+  }
+}
+
+int launch_candidate_loss_fwd(const float *gt, const float *pred, const float *weights, int BV,
+                              int C, int V, int G, float *all_loss, long long *min_idx,
+                              float *view_loss, cudaStream_t s) {
+  candidate_loss_fwd_kernel<<<BV, kLossThreads, 0, s>>>(gt, pred, weights, C, V, G, all_loss,
+                                                           min_idx, view_loss);
+  return check_launch("candidate_loss_fwd");
+}
+
+int launch_candidate_loss_bwd(const float *gt, const float *pred, const float *weights,
+                              const long long *min_idx, const float *upstream, float coeff, int BV,
+                              int C, int V, int G, float *g_pred, cudaStream_t s) {
+  candidate_loss_bwd_kernel<<<BV * C, kLossThreads, 0, s>>>(gt, pred, weights, min_idx, upstream,
+                                                            coeff, C, V, G, g_pred);
+  return check_launch("candidate_loss_bwd");
+}
+
+int candidate_loss_max_candidates() { return kMaxCandidates; }
+
+}  // namespace dpc

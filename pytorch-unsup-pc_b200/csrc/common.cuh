@@ -175,4 +175,17 @@ int launch_depth_from_probs(const float *probs, float *depth, int P, int Vz, int
 int launch_depth_from_probs_bwd(const float *g_depth, float *g_probs, int P, int Vz, int V,
                                 float cam_dist, float max_depth, cudaStream_t s);
 
+// ---- candidate-selection projection loss (candidate_loss.cu) -----------------
+int candidate_loss_max_candidates();
+int launch_candidate_loss_fwd(const float *gt, const float *pred, const float *weights, int BV,
+                              int C, int V, int G, float *all_loss, long long *min_idx,
+                              float *view_loss, cudaStream_t s);
+int launch_candidate_loss_bwd(const float *gt, const float *pred, const float *weights,
+                              const long long *min_idx, const float *upstream, float coeff, int BV,
+                              int C, int V, int G, float *g_pred, cudaStream_t s);
+
+// ---- nearest neighbour for the Chamfer evaluation (chamfer.cu) -----------------
+int launch_nn_search(const float *src, int N, const float *tgt, int M, unsigned long long *keys,
+                     float *proj, float *min_dist, long long *idx, cudaStream_t s);
+
 }  // namespace dpc
