@@ -365,22 +365,63 @@ def run_b200(args, rank, world, local_rank):
                        "g_quat": gq, "g_scale": gs}, out_host)
         assert pipe.h2d_bytes == h2d and pipe.d2h_bytes == d2h
 
-    e2e_mode = "eager"
-    if args.graph:
-        # E2E_GRAPH_STEPS consecutive e2e steps (each with its own H2D and D2H copies) captured
-        # once with the public GraphedSteps helper and replayed: the eager loop is bound by
-        # the host (~0.35 ms of Python / autograd-engine work per ~0.2 ms step)
-        gs = dpc.GraphedSteps(step_e2e, E2E_GRAPH_STEPS, dev, pipe=pipe, warmup=2)
-        reps = (args.steps + E2E_GRAPH_STEPS - 1) // E2E_GRAPH_STEPS
+    def measure_e2e(step_fn):
+        if args.graph:
+            # E2E_GRAPH_STEPS consecutive e2e steps (each with its own H2D and D2H copies) captured
+            # once with the public GraphedSteps helper and replayed: the eager loop is bound by
+            # the host (~0.35 ms of Python / autograd-engine work per ~0.2 ms step)
+            gs = dpc.GraphedSteps(step_fn, E2E_GRAPH_STEPS, dev, pipe=pipe, warmup=2)
+            reps = (args.steps + E2E_GRAPH_STEPS - 1) // E2E_GRAPH_STEPS
 
-        def replay_e2e(i):
-            if i % E2E_GRAPH_STEPS == 0:
-                gs.replay()
-        ms_e2e = timed(replay_e2e, reps * E2E_GRAPH_STEPS, 2 * E2E_GRAPH_STEPS) * args.steps / (
-            reps * E2E_GRAPH_STEPS)
-        e2e_mode = "GraphedSteps(%d steps per CUDA graph)" % E2E_GRAPH_STEPS
-    else:
-        ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), join=(pipe.h2d, pipe.d2h))
+            def replay_e2e(i):
+                if i % E2E_GRAPH_STEPS == 0:
+                    gs.replay()
+            ms = timed(replay_e2e, reps * E2E_GRAPH_STEPS, 2 * E2E_GRAPH_STEPS) * args.steps / (
+                reps * E2E_GRAPH_STEPS)
+            mode = "GraphedSteps(%d steps per CUDA graph)" % E2E_GRAPH_STEPS
+        else:
+            ms = timed(step_fn, args.steps, max(args.warmup, 3), join=(pipe.h2d, pipe.d2h))
+            mode = "eager"
+        pipe.drain()
+        return ms, mode
+
+    ms_e2e, e2e_mode = measure_e2e(step_e2e)
+
+    # ---- (2b) the same step through the replica-aware API (next row f2): the host holds the
+    # UN-replicated clouds (P / candidates of them), the kernels read cloud b // candidates, and
+    # the cloud gradient comes back summed over the candidates -- 4x fewer point bytes each way
+    R = args.candidates
+    e2e_rep = None
+    if R > 1 and P % R == 0:
+        B = P // R
+        host_rep = [{"points": h["points"][::R].contiguous().pin_memory(), "quat": h["quat"],
+                     "scale": h["scale"]} for h in host]
+        out_host_rep = dict(out_host, g_points=torch.empty(B, N, 3).pin_memory())
+        h2d_rep = sum(host_rep[0][k].numel() * 4 for k in ("points", "quat", "scale"))
+        d2h_rep = sum(v.numel() * 4 for v in out_host_rep.values())
+
+        def step_e2e_rep(i):
+            h = host_rep[i % N_INPUT_SETS]
+            din = pipe.upload({"points": h["points"], "quat": h["quat"], "scale": h["scale"]})
+            pts = din["points"].detach().requires_grad_()
+            quat = din["quat"].detach().requires_grad_()
+            scale = din["scale"].detach().requires_grad_()
+            d = devin[i % N_INPUT_SETS]
+            out = dpc.pointcloud_project_replicated(cfg, pts, quat, None, None, kern,
+                                                    scaling_factor=scale)
+            gp, gq, gs = torch.autograd.grad([out["proj"], out["proj_depth"]], [pts, quat, scale],
+                                             [d["g_mask"], d["g_depth"]])
+            pipe.download({"mask": out["proj"], "depth": out["proj_depth"], "g_points": gp,
+                           "g_quat": gq, "g_scale": gs}, out_host_rep)
+            assert pipe.h2d_bytes == h2d_rep and pipe.d2h_bytes == d2h_rep
+
+        ms_rep, mode_rep = measure_e2e(step_e2e_rep)
+        e2e_rep = {"value": world * P * args.steps / (ms_rep * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": h2d_rep, "d2h_bytes_per_step": d2h_rep,
+                   "ms_per_step": ms_rep / args.steps,
+                   "api": "pytorch_unsup_pc_b200.pointcloud_project_replicated: %d clouds x %d pose "
+                          "candidates per step, cloud gradient summed over the candidates in the "
+                          "kernels" % (B, R), "mode": mode_rep}
     pipe.drain()
     # ---- (3) per-stage CUDA-event timings for the roofline ----
     stage_ms = (ctypes.c_float * len(_lib.PROFILE_STAGES))()
@@ -439,6 +480,7 @@ def run_b200(args, rank, world, local_rank):
                        "host copies through pytorch_unsup_pc_b200.HostPipeline (3 streams: this "
                        "step's H2D / kernels / D2H overlap the neighbouring steps')",
                 "mode": e2e_mode},
+        "e2e_replica_aware": e2e_rep,
         "gpu_launches": (6 if args.global_grid else 7) * args.steps,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
@@ -465,6 +507,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--candidates", type=int, default=4,
+                    help="pose candidates per cloud for the e2e_replica_aware leg (workload A: 16 x 4)")
     ap.add_argument("--global-grid", action="store_true",
                     help="A/B: keep the raw grid in global memory (memset + atomic scatter, grid "
                          "gather) instead of the default plane-local path")

@@ -42,7 +42,7 @@ extern "C" {
 #define DPC_API
 #endif
 
-#define DPC_B200_VERSION 110
+#define DPC_B200_VERSION 120
 #define DPC_MAX_TAPS 21
 
 typedef enum {
@@ -177,6 +177,68 @@ DPC_API int dpc_candidate_loss_bwd(int BV, int C, int V, int G, const float *gt,
                            const float *weights /*NULL ok*/, const int64_t *min_idx,
                            const float *upstream /*NULL ok*/, float coeff, float *g_pred,
                            void *stream);
+
+/* ---- f2 (next row): replica-aware projection + point dropout on the device --
+ * Reference: models/model_pc_to.py:47-56 tf_repeat_0 and :302-306 (every cloud
+ * is materialised step_size x num_candidates times before the projection),
+ * :254-258 + util/point_cloud_to.py:269-295 pc_point_dropout (host numpy
+ * sampler np.random.choice(N, M, replace=False) per replica + index gather),
+ * and the autograd of both (index backward, sum over replicas).
+ *
+ * points is the UN-replicated cloud tensor [P/replicas, N_src, 3]; projection b
+ * reads cloud b / replicas (tf_repeat_0 order: the replicas of a cloud are
+ * adjacent).  sel [P,N] int32 (NULL ok) lists, per projection, the N cloud
+ * points that survive the dropout -- DISTINCT indices in [0, N_src), as the
+ * reference samples them; without it N == N_src.  Everything else is as in
+ * dpc_project_fwd (p->N = points per projection after dropout). */
+DPC_API int dpc_project_replicated_fwd(const dpc_params *p, int replicas, int N_src,
+                    const int32_t *sel /*NULL ok*/,
+                    const float *points, const float *quat,
+                    const float *trans /*NULL ok*/, const float *focal /*NULL ok*/,
+                    const float *scale /*NULL ok*/,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz, int scatter_mode,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells /*NULL ok*/,
+                    float *mask, float *depth,
+                    float *voxels /*NULL ok*/, float *probs /*NULL ok*/,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* As dpc_project_bwd, but g_points is the gradient of the cloud tensor
+ * [P/replicas, N_src, 3]: the per-replica point gradients (g_points_rep
+ * [P,N,3], scratch) are summed over the replicas in replica order and routed
+ * through the selection (dropped points get 0) -- deterministic, no atomics.
+ * inv_scratch: [P,N_src] int32, needed when sel != NULL. */
+DPC_API int dpc_project_replicated_bwd(const dpc_params *p, int replicas, int N_src,
+                    const int32_t *sel /*NULL ok*/,
+                    const float *points, const float *quat,
+                    const float *trans, const float *focal, const float *scale,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz,
+                    const float *grid_b, const uint32_t *clamp_bits, const void *cells /*NULL ok*/,
+                    const float *g_mask /*NULL ok*/, const float *g_depth /*NULL ok*/,
+                    const float *g_probs /*NULL ok*/, const float *g_voxels /*NULL ok*/,
+                    const float *g_tr_pc /*NULL ok*/,
+                    float *g_grid, float *g_points_rep, int32_t *inv_scratch /*NULL ok*/,
+                    float *g_points, float *g_quat, float *g_trans,
+                    float *g_focal, float *g_scale,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* The sampler of pc_point_dropout (point_cloud_to.py:275-283) on the device:
+ * sel [P,M] = a uniformly random M-subset of [0, N_src) per projection, in
+ * ascending order, a pure function of (seed, projection index).  Same
+ * distribution as np.random.choice(N_src, M, replace=False) up to the order
+ * inside the subset, which the projection does not depend on. */
+DPC_API int dpc_point_dropout_indices(int P, int N_src, int M, uint64_t seed, int32_t *sel,
+                              void *stream);
+/* The gather of pc_point_dropout (select_3d, point_cloud_to.py:266-267) as a
+ * stand-alone op: out [P,M,C] = points [P/replicas, N_src, C] at sel [P,M]
+ * (C <= 4: xyz or rgb). */
+DPC_API int dpc_select_points(int P, int replicas, int N_src, int M, int C, const float *points,
+                      const int32_t *sel, float *out, void *stream);
+/* Its adjoint fused with the adjoint of tf_repeat_0: g_cloud [P/replicas,
+ * N_src, C] = sum over the replicas of g_rep [P,M,C] routed through sel
+ * (sel == NULL: M == N_src, identity routing).  inv_scratch as above. */
+DPC_API int dpc_replica_reduce(int P, int replicas, int N_src, int M, int C, const float *g_rep,
+                       const int32_t *sel /*NULL ok*/, int32_t *inv_scratch /*NULL ok*/,
+                       float *g_cloud, void *stream);
 
 /* ---- f4 (next row): util/point_cloud_distance.py:25-40 point_cloud_distance
  * (the kernel of run/eval_chamfer_to.py:24-44 compute_distance) -------------

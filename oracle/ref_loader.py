@@ -152,3 +152,31 @@ def ref_point_cloud_distance(Vs, Vt):
     load()
     import util.point_cloud_distance as pcd
     return pcd.point_cloud_distance(Vs, Vt)
+
+
+def ref_project_replicated(cfg, point_cloud, transform, step_size, num_candidates, keep_prob,
+                           numpy_seed, predicted_translation=None, kernel=None,
+                           scaling_factor=None, focal_length=None):
+    """The reference's own replication + dropout + projection, in the order of
+    ``ModelPointCloud.forward`` / ``compute_projection`` (models/model_pc_to.py:302-306,
+    254-265): ``tf_repeat_0`` by views then by candidates (its own function), its own
+    ``pc_point_dropout`` with numpy's global RNG seeded to ``numpy_seed``, ``ref_project``.
+    Returns (outputs, indices [P,M] int64 recovered by running the same sampler on an
+    index-carrying tensor, or None)."""
+    m = load()
+    import models.model_pc_to as model_pc
+    pts = model_pc.tf_repeat_0(point_cloud, step_size)
+    if num_candidates > 1:
+        pts = model_pc.tf_repeat_0(pts, num_candidates)
+    indices = None
+    if keep_prob != 1:
+        P, N = pts.shape[0], pts.shape[1]
+        np.random.seed(numpy_seed)
+        carrier = torch.arange(N, dtype=torch.float64).reshape(1, N, 1).repeat(P, 1, 1)
+        picked, _ = m["pc_to"].pc_point_dropout(carrier, None, keep_prob)
+        indices = picked[:, :, 0].long()
+        np.random.seed(numpy_seed)
+        pts, _ = m["pc_to"].pc_point_dropout(pts, None, keep_prob)
+    out = ref_project(cfg, pts, transform, predicted_translation, kernel, scaling_factor,
+                      focal_length)
+    return out, indices

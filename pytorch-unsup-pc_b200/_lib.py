@@ -55,6 +55,16 @@ SIGNATURES = {
                        + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
                        + [c_void_p] * 3 + [c_void_p] * 5 + [c_void_p] * 6
                        + [c_void_p, c_size_t, c_void_p],
+    "dpc_project_replicated_fwd": [_P, c_int, c_int, c_void_p] + [c_void_p] * 5
+                       + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
+                       + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p],
+    "dpc_project_replicated_bwd": [_P, c_int, c_int, c_void_p] + [c_void_p] * 5
+                       + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
+                       + [c_void_p] * 3 + [c_void_p] * 5 + [c_void_p] * 8
+                       + [c_void_p, c_size_t, c_void_p],
+    "dpc_point_dropout_indices": [c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p],
+    "dpc_select_points": [c_int] * 5 + [c_void_p] * 3 + [c_void_p],
+    "dpc_replica_reduce": [c_int] * 5 + [c_void_p] * 4 + [c_void_p],
     "dpc_candidate_loss_fwd": [c_int] * 4 + [c_void_p] * 6 + [c_void_p],
     "dpc_candidate_loss_bwd": [c_int] * 4 + [c_void_p] * 5 + [ctypes.c_float, c_void_p, c_void_p],
     "dpc_point_cloud_distance": [c_int, c_int] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p],

@@ -116,14 +116,34 @@ static int check_ws(const dpc_params *p, void *ws, size_t bytes) {
     if (_e != DPC_OK) return _e; \
   } while (0)
 
+// f2: how the projections address an un-replicated cloud tensor (replicas == 0: plain [P,N,3])
+struct Replica {
+  int replicas = 0, N_src = 0;
+  const int *sel = nullptr;
+};
+
 static PoseArgs pose_args(const dpc_params *p, const float *points, const float *quat,
-                          const float *trans, const float *focal) {
+                          const float *trans, const float *focal, const Replica &rep = Replica()) {
   PoseArgs a;
   a.points = points; a.quat = quat; a.trans = trans; a.focal = focal;
   a.P = p->P; a.N = p->N; a.Vz = p->Vz; a.V = p->V;
   a.cam_dist = p->camera_distance;
   a.focal_const = p->focal_length;
+  a.replicas = rep.replicas; a.N_src = rep.N_src; a.sel = rep.sel;
   return a;
+}
+
+static int check_replica(const dpc_params *p, int replicas, int N_src, const int32_t *sel) {
+  if (replicas < 1 || p->P % replicas != 0) {
+    set_error("replicas=%d must be >= 1 and divide P=%d", replicas, p->P);
+    return DPC_ERR_ARG;
+  }
+  if (sel ? (p->N > N_src) : (p->N != N_src)) {
+    set_error("N=%d points per projection do not fit a cloud of N_src=%d points (%s)", p->N, N_src,
+              sel ? "with a selection N <= N_src" : "without a selection N == N_src");
+    return DPC_ERR_ARG;
+  }
+  return DPC_OK;
 }
 
 static DrcArgs drc_args(const dpc_params *p, const float *grid, const float *scale) {
@@ -303,6 +323,7 @@ struct FwdPtrs {
   const float *points, *quat, *trans, *focal, *scale;
   float *tr_pc, *grid_b; uint32_t *bits; float *mask, *depth, *voxels, *probs;
   void *cells;
+  Replica rep;
 };
 
 // The plane-local path packs (n, iy, ix) into 32 bits and bins by a z-cell byte.
@@ -327,9 +348,10 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   dpc_params sp = *p;
   sp.P = n;
   const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V, I = (size_t)p->V * p->V;
+  // (a replica-aware pass always covers the whole batch: b0 == 0)
   const PoseArgs pa = pose_args(&sp, q.points + b0 * N3, q.quat + b0 * 4,
                                 q.trans ? q.trans + b0 * 3 : nullptr,
-                                q.focal ? q.focal + b0 : nullptr);
+                                q.focal ? q.focal + b0 : nullptr, q.rep);
   float *grid = q.grid_b + b0 * G;
   float *tr_pc = q.tr_pc ? q.tr_pc + b0 * N3 : nullptr;
   stage_mark(s);
@@ -368,7 +390,8 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   return DPC_OK;
 }
 
-int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
+static int project_fwd_impl(const dpc_params *p, const Replica &rep, const float *points,
+                    const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
                     const float *ty, int ky, const float *tz, int kz, int scatter_mode,
                     float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells, float *mask,
@@ -392,8 +415,8 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
   }
   cudaStream_t s = (cudaStream_t)stream;
   const FwdPtrs q{points, quat, trans, focal, scale, tr_pc, grid_b, clamp_bits, mask, depth, voxels,
-                  probs, cells};
-  const int chunk = chunk_size(p);
+                  probs, cells, rep};
+  const int chunk = rep.replicas > 0 ? p->P : chunk_size(p);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   if (!pl) return project_fwd_range(p, 0, p->P, q, tx, kx, ty, ky, tz, kz, scatter_mode, w, s);
   cudaEventRecord(pl->fork, s);
@@ -410,11 +433,39 @@ int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
   return rc;
 }
 
+int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
+                    const float *focal, const float *scale, const float *tx, int kx,
+                    const float *ty, int ky, const float *tz, int kz, int scatter_mode,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells, float *mask,
+                    float *depth, float *voxels, float *probs, void *workspace,
+                    size_t workspace_bytes, void *stream) {
+  return project_fwd_impl(p, Replica(), points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz,
+                          scatter_mode, tr_pc, grid_b, clamp_bits, cells, mask, depth, voxels, probs,
+                          workspace, workspace_bytes, stream);
+}
+
+int dpc_project_replicated_fwd(const dpc_params *p, int replicas, int N_src, const int32_t *sel,
+                    const float *points, const float *quat, const float *trans,
+                    const float *focal, const float *scale, const float *tx, int kx,
+                    const float *ty, int ky, const float *tz, int kz, int scatter_mode,
+                    float *tr_pc, float *grid_b, uint32_t *clamp_bits, void *cells, float *mask,
+                    float *depth, float *voxels, float *probs, void *workspace,
+                    size_t workspace_bytes, void *stream) {
+  DPC_TRY(check_params(p, true));
+  DPC_TRY(check_replica(p, replicas, N_src, sel));
+  Replica rep;
+  rep.replicas = replicas; rep.N_src = N_src; rep.sel = sel;
+  return project_fwd_impl(p, rep, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz,
+                          scatter_mode, tr_pc, grid_b, clamp_bits, cells, mask, depth, voxels, probs,
+                          workspace, workspace_bytes, stream);
+}
+
 struct BwdPtrs {
   const float *points, *quat, *trans, *focal, *scale, *grid_b; const uint32_t *bits;
   const float *g_mask, *g_depth, *g_probs, *g_voxels, *g_tr_pc;
   float *g_grid, *g_points, *g_quat, *g_trans, *g_focal, *g_scale;
   void *cells;
+  Replica rep;
 };
 
 static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &q, const float *tx,
@@ -425,7 +476,7 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
   const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V, I = (size_t)p->V * p->V;
   const PoseArgs pa = pose_args(&sp, q.points + b0 * N3, q.quat + b0 * 4,
                                 q.trans ? q.trans + b0 * 3 : nullptr,
-                                q.focal ? q.focal + b0 : nullptr);
+                                q.focal ? q.focal + b0 : nullptr, q.rep);
   float *g_grid = q.g_grid + b0 * G;
   DrcArgs da = drc_args(&sp, q.grid_b + b0 * G, q.scale ? q.scale + b0 : nullptr);
   da.P_total = p->P;
@@ -479,7 +530,8 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
   return DPC_OK;
 }
 
-int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
+static int project_bwd_impl(const dpc_params *p, const Replica &rep, const float *points,
+                    const float *quat, const float *trans,
                     const float *focal, const float *scale, const float *tx, int kx,
                     const float *ty, int ky, const float *tz, int kz, const float *grid_b,
                     const uint32_t *clamp_bits, const void *cells, const float *g_mask,
@@ -501,8 +553,8 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
   if (!plane_local_ok(p) || p->V > 64) cells = nullptr;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
                   g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
-                  const_cast<void *>(cells)};
-  const int chunk = chunk_size(p);
+                  const_cast<void *>(cells), rep};
+  const int chunk = rep.replicas > 0 ? p->P : chunk_size(p);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   int rc = DPC_OK;
   if (!pl) {
@@ -520,6 +572,78 @@ int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat,
     }
   }
   return rc;
+}
+
+int dpc_project_bwd(const dpc_params *p, const float *points, const float *quat, const float *trans,
+                    const float *focal, const float *scale, const float *tx, int kx,
+                    const float *ty, int ky, const float *tz, int kz, const float *grid_b,
+                    const uint32_t *clamp_bits, const void *cells, const float *g_mask,
+                    const float *g_depth, const float *g_probs, const float *g_voxels,
+                    const float *g_tr_pc, float *g_grid, float *g_points, float *g_quat,
+                    float *g_trans, float *g_focal, float *g_scale, void *workspace,
+                    size_t workspace_bytes, void *stream) {
+  return project_bwd_impl(p, Replica(), points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz,
+                          grid_b, clamp_bits, cells, g_mask, g_depth, g_probs, g_voxels, g_tr_pc,
+                          g_grid, g_points, g_quat, g_trans, g_focal, g_scale, workspace,
+                          workspace_bytes, stream);
+}
+
+// ---- f2: replica-aware projection + point dropout on the device ----------------
+int dpc_project_replicated_bwd(const dpc_params *p, int replicas, int N_src, const int32_t *sel,
+                    const float *points, const float *quat, const float *trans,
+                    const float *focal, const float *scale, const float *tx, int kx,
+                    const float *ty, int ky, const float *tz, int kz, const float *grid_b,
+                    const uint32_t *clamp_bits, const void *cells, const float *g_mask,
+                    const float *g_depth, const float *g_probs, const float *g_voxels,
+                    const float *g_tr_pc, float *g_grid, float *g_points_rep, int32_t *inv_scratch,
+                    float *g_points, float *g_quat,
+                    float *g_trans, float *g_focal, float *g_scale, void *workspace,
+                    size_t workspace_bytes, void *stream) {
+  DPC_TRY(check_params(p, true));
+  DPC_TRY(check_replica(p, replicas, N_src, sel));
+  DPC_REQUIRE(g_points_rep); DPC_REQUIRE(g_points);
+  if (sel) DPC_REQUIRE(inv_scratch);
+  Replica rep;
+  rep.replicas = replicas; rep.N_src = N_src; rep.sel = sel;
+  DPC_TRY(project_bwd_impl(p, rep, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz,
+                           grid_b, clamp_bits, cells, g_mask, g_depth, g_probs, g_voxels, g_tr_pc,
+                           g_grid, g_points_rep, g_quat, g_trans, g_focal, g_scale, workspace,
+                           workspace_bytes, stream));
+  // autograd of tf_repeat_0 (sum over the replicas) and of the dropout gather, in one pass
+  return launch_replica_reduce(g_points_rep, sel, inv_scratch, p->P, replicas, N_src, p->N, 3,
+                               g_points, (cudaStream_t)stream);
+}
+
+static int check_select_args(int P, int replicas, int N_src, int M, int C) {
+  if (P < 1 || replicas < 1 || P % replicas != 0 || N_src < 1 || M < 1 || M > N_src || C < 1 || C > 4) {
+    set_error("point selection: need P=%d >= 1, replicas=%d dividing P, 1 <= M=%d <= N_src=%d, "
+              "1 <= channels=%d <= 4", P, replicas, M, N_src, C);
+    return DPC_ERR_ARG;
+  }
+  return DPC_OK;
+}
+
+int dpc_point_dropout_indices(int P, int N_src, int M, uint64_t seed, int32_t *sel, void *stream) {
+  DPC_TRY(check_select_args(P, 1, N_src, M, 1));
+  DPC_REQUIRE(sel);
+  return launch_dropout_select(P, N_src, M, seed, sel, (cudaStream_t)stream);
+}
+
+int dpc_select_points(int P, int replicas, int N_src, int M, int C, const float *points,
+                      const int32_t *sel, float *out, void *stream) {
+  DPC_TRY(check_select_args(P, replicas, N_src, M, C));
+  DPC_REQUIRE(points); DPC_REQUIRE(sel); DPC_REQUIRE(out);
+  return launch_select_points(points, sel, P, replicas, N_src, M, C, out, (cudaStream_t)stream);
+}
+
+int dpc_replica_reduce(int P, int replicas, int N_src, int M, int C, const float *g_rep,
+                       const int32_t *sel, int32_t *inv_scratch, float *g_cloud, void *stream) {
+  DPC_TRY(check_select_args(P, replicas, N_src, M, C));
+  DPC_REQUIRE(g_rep); DPC_REQUIRE(g_cloud);
+  if (sel) DPC_REQUIRE(inv_scratch);
+  if (!sel && M != N_src) { set_error("replica_reduce: without a selection M must equal N_src"); return DPC_ERR_ARG; }
+  return launch_replica_reduce(g_rep, sel, inv_scratch, P, replicas, N_src, M, C, g_cloud,
+                               (cudaStream_t)stream);
 }
 
 // ---- f1: candidate-selection projection loss --------------------------------

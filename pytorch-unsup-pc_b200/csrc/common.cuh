@@ -51,7 +51,22 @@ struct PoseArgs {
   const float *points, *quat, *trans, *focal;
   int P, N, Vz, V;
   double cam_dist, focal_const;
+  // Replica-aware addressing (next row f2; model_pc_to.py:47-56 tf_repeat_0, point_cloud_to.py:
+  // 269-295 pc_point_dropout): with replicas >= 1, `points` is the UN-replicated [P/replicas,
+  // N_src, 3] cloud tensor, projection b reads cloud b / replicas, and point n of the projection
+  // is cloud point sel[b][n] (sel == NULL: n itself, N == N_src).  replicas == 0: points is
+  // [P,N,3] as the reference holds it.
+  const int *sel = nullptr;
+  int replicas = 0, N_src = 0;
 };
+#ifdef __CUDACC__
+// float offset of point n of projection b in a.points
+__device__ __forceinline__ size_t point_offset(const PoseArgs &a, int b, int n) {
+  if (a.replicas == 0) return ((size_t)b * a.N + n) * 3;
+  const int src = a.sel ? __ldg(a.sel + (size_t)b * a.N + n) : n;
+  return ((size_t)(b / a.replicas) * a.N_src + src) * 3;
+}
+#endif
 
 // Per-point cell records (saved by the forward for the backward): the grid cell
 // and trilinear fractions of every point, derived ONCE from the fp64 pose so
@@ -174,6 +189,14 @@ int launch_depth_from_probs(const float *probs, float *depth, int P, int Vz, int
                             float cam_dist, float max_depth, cudaStream_t s);
 int launch_depth_from_probs_bwd(const float *g_depth, float *g_probs, int P, int Vz, int V,
                                 float cam_dist, float max_depth, cudaStream_t s);
+
+// ---- replica-aware projection + device point dropout (replica.cu) -------------
+int launch_dropout_select(int P, int N_src, int M, uint64_t seed, int *sel, cudaStream_t s);
+int launch_select_points(const float *points, const int *sel, int P, int R, int N_src, int M, int C,
+                         float *out, cudaStream_t s);
+// inv: [P,N_src] int scratch, used when sel != NULL
+int launch_replica_reduce(const float *g_rep, const int *sel, int *inv, int P, int R, int N_src,
+                          int M, int C, float *g_cloud, cudaStream_t s);
 
 // ---- candidate-selection projection loss (candidate_loss.cu) -----------------
 int candidate_loss_max_candidates();

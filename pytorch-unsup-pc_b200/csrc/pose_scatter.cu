@@ -49,8 +49,8 @@ pose_scatter_kernel(PoseArgs a, float *__restrict__ tr_pc, float *__restrict__ g
     t2 = a.trans[3 * b + 2];
   }
   const double f = a.focal ? (double)a.focal[b] : a.focal_const;
-  const size_t pi = ((size_t)b * a.N + n) * 3;
-  const float p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
+  const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+  const float p0 = a.points[si], p1 = a.points[si + 1], p2 = a.points[si + 2];
   const PosePoint pp = pose_point(q, p0, p1, p2, has_t, t0, t1, t2, f, a.cam_dist);
   if (WRITE_TRPC) {
     tr_pc[pi] = (float)pp.u0;
@@ -100,8 +100,8 @@ pose_cells_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
     t2 = a.trans[3 * b + 2];
   }
   const double f = a.focal ? (double)a.focal[b] : a.focal_const;
-  const size_t pi = ((size_t)b * a.N + n) * 3;
-  const PosePoint pp = pose_point(q, a.points[pi], a.points[pi + 1], a.points[pi + 2], has_t, t0,
+  const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+  const PosePoint pp = pose_point(q, a.points[si], a.points[si + 1], a.points[si + 2], has_t, t0,
                                   t1, t2, f, a.cam_dist);
   if (WRITE_TRPC) {
     tr_pc[pi] = (float)pp.u0;
@@ -393,8 +393,8 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     for (int it = 0; it < kBwdPts; ++it) {
       const int n = (blockIdx.x * kBwdPts + it) * kBwdThreads + threadIdx.x;
       if (n >= a.N) continue;
-      const size_t pi = ((size_t)b * a.N + n) * 3;
-      const float p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
+      const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+      const float p0 = a.points[si], p1 = a.points[si + 1], p2 = a.points[si + 2];
       // p' = q^ (0,p) q^* (+ t), zc = p'0 + camera distance
       const float aw = -(vx * p0 + vy * p1 + vz * p2);
       const float ax = w * p0 + vy * p2 - vz * p1;
@@ -452,8 +452,8 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
   for (int it = 0; it < kBwdPts; ++it) {
     const int n = (blockIdx.x * kBwdPts + it) * kBwdThreads + threadIdx.x;
     if (n >= a.N) continue;
-    const size_t pi = ((size_t)b * a.N + n) * 3;
-    const double p0 = a.points[pi], p1 = a.points[pi + 1], p2 = a.points[pi + 2];
+    const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+    const double p0 = a.points[si], p1 = a.points[si + 1], p2 = a.points[si + 2];
     const PosePoint pp = pose_point(q, (float)p0, (float)p1, (float)p2, has_t, t0, t1, t2, f,
                                     a.cam_dist);
     double gu0 = 0, gu1 = 0, gu2 = 0;

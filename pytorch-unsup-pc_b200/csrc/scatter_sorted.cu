@@ -46,7 +46,8 @@ __device__ __forceinline__ Cell point_cell(const PointSource &src, int b, int n,
     const float t0 = has_t ? a.trans[3 * b] : 0.f, t1 = has_t ? a.trans[3 * b + 1] : 0.f,
                 t2 = has_t ? a.trans[3 * b + 2] : 0.f;
     const double f = a.focal ? (double)a.focal[b] : a.focal_const;
-    const PosePoint pp = pose_point(q, a.points[pi], a.points[pi + 1], a.points[pi + 2], has_t, t0,
+    const size_t si = point_offset(a, b, n);
+    const PosePoint pp = pose_point(q, a.points[si], a.points[si + 1], a.points[si + 2], has_t, t0,
                                     t1, t2, f, a.cam_dist);
     u0 = pp.u0; u1 = pp.u1; u2 = pp.u2;
     if (tr_out) {

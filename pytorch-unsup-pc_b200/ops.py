@@ -134,7 +134,9 @@ class ProjectFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, points, quat, trans, focal, scale, params, taps, want_voxels, want_probs,
-                mode, plane_local=True):
+                mode, plane_local=True, rep=None):
+        # rep = (replicas, N_src, sel) for the replica-aware entry points (next row f2): points
+        # is then the un-replicated [P/replicas, N_src, 3] cloud tensor; None = plain [P,N,3]
         lib = _lib.load()
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
@@ -155,15 +157,21 @@ class ProjectFn(torch.autograd.Function):
         grid_b, bits = ctypes.c_void_p(base), ctypes.c_void_p(base + n_grid)
         cells = ctypes.c_void_p(base + n_grid + n_bits) if use_cells else None
         ws = _workspace(params, dev)
-        with _on_device(dev):
-            st = lib.dpc_project_fwd(
-                ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
+        tail = (_ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
                 _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), grid_b, bits,
                 cells, _ptr(mask), _ptr(depth), _ptr(voxels), _ptr(probs), _ptr(ws),
                 ws.numel(), _stream(dev))
+        with _on_device(dev):
+            if rep is None:
+                st = lib.dpc_project_fwd(ctypes.byref(params), *tail)
+            else:
+                st = lib.dpc_project_replicated_fwd(ctypes.byref(params), int(rep[0]), int(rep[1]),
+                                                    _ptr(rep[2]), *tail)
         _lib.check(st, "project_fwd")
-        ctx.save_for_backward(points, quat, trans, focal, scale, state)
+        ctx.save_for_backward(points, quat, trans, focal, scale, state,
+                              None if rep is None else rep[2])
         ctx.params, ctx.taps = params, taps
+        ctx.rep = None if rep is None else (int(rep[0]), int(rep[1]))
         ctx.state_layout = (n_grid, n_bits, use_cells)
         ctx.set_materialize_grads(False)
         return mask, depth, tr_pc, voxels, probs
@@ -171,7 +179,7 @@ class ProjectFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mask, g_depth, g_trpc, g_voxels, g_probs):
         lib = _lib.load()
-        points, quat, trans, focal, scale, state = ctx.saved_tensors
+        points, quat, trans, focal, scale, state, sel = ctx.saved_tensors
         n_grid, n_bits, use_cells = ctx.state_layout
         base = state.data_ptr()
         grid_b, bits = ctypes.c_void_p(base), ctypes.c_void_p(base + n_grid)
@@ -186,21 +194,32 @@ class ProjectFn(torch.autograd.Function):
         g_voxels = _f32(g_voxels, "g_voxels", (P, Vz, V, V))
         g_probs = _f32(g_probs, "g_probs", (Vz + 1, P, V, V))
         g_grid = _scratch("g_grid", n_grid, dev)      # dead after this call
-        g_points = torch.empty(P, N, 3, **f32)
+        g_points = torch.empty(P, N, 3, **f32) if ctx.rep is None else None
         g_quat = torch.empty(P, 4, **f32)
         g_trans = torch.empty(P, 3, **f32) if trans is not None else None
         g_focal = torch.empty(P, **f32) if focal is not None else None
         g_scale = torch.empty(P, **f32) if scale is not None else None
         ws = _workspace(params, dev)
-        with _on_device(dev):
-            st = lib.dpc_project_bwd(
-                ctypes.byref(params), _ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
+        head = (_ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
                 _ptr(scale), *_tap_args(ctx.taps), grid_b, bits, cells,
-                _ptr(g_mask), _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid),
-                _ptr(g_points), _ptr(g_quat), _ptr(g_trans), _ptr(g_focal), _ptr(g_scale),
+                _ptr(g_mask), _ptr(g_depth), _ptr(g_probs), _ptr(g_voxels), _ptr(g_trpc), _ptr(g_grid))
+        tail = (_ptr(g_quat), _ptr(g_trans), _ptr(g_focal), _ptr(g_scale),
                 _ptr(ws), ws.numel(), _stream(dev))
+        with _on_device(dev):
+            if ctx.rep is None:
+                st = lib.dpc_project_bwd(ctypes.byref(params), *head, _ptr(g_points), *tail)
+            else:
+                # per-replica point gradients are scratch; the gradient of the CLOUD tensor is
+                # their sum over the replicas routed through the dropout selection
+                R, N_src = ctx.rep
+                g_rep = _scratch("g_rep", P * N * 12, dev)
+                inv = _scratch("inv", P * N_src * 4, dev) if sel is not None else None
+                g_points = torch.empty(P // R, N_src, 3, **f32)
+                st = lib.dpc_project_replicated_bwd(
+                    ctypes.byref(params), R, N_src, _ptr(sel), *head, _ptr(g_rep), _ptr(inv),
+                    _ptr(g_points), *tail)
         _lib.check(st, "project_bwd")
-        return (g_points, g_quat, g_trans, g_focal, g_scale, None, None, None, None, None, None)
+        return (g_points, g_quat, g_trans, g_focal, g_scale) + (None,) * 7
 
 
 class PoseFn(torch.autograd.Function):
@@ -370,3 +389,56 @@ class DepthFromProbsFn(torch.autograd.Function):
                                               _stream(dev))
         _lib.check(st, "depth_from_probs_bwd")
         return g_probs, None
+
+
+def dropout_indices(P, N_src, M, seed, device):
+    """sel [P,M] int32: a uniformly random M-subset of range(N_src) per projection, ascending,
+    a pure function of (seed, projection index) -- the device replacement of the reference's
+    numpy sampler (point_cloud_to.py:275-283)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("dropout_indices needs a CUDA device: dpc_b200 has no CPU fallback")
+    sel = torch.empty(P, M, dtype=torch.int32, device=device)
+    with _on_device(device):
+        st = lib.dpc_point_dropout_indices(int(P), int(N_src), int(M),
+                                           ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(sel),
+                                           _stream(device))
+    _lib.check(st, "point_dropout_indices")
+    return sel
+
+
+class SelectPointsFn(torch.autograd.Function):
+    """select_3d (point_cloud_to.py:266-267) on a cloud tensor shared by `replicas`
+    projections: out [P,M,C] = data [P/replicas, N_src, C] at sel [P,M]; backward sums over the
+    replicas in replica order (deterministic)."""
+
+    @staticmethod
+    def forward(ctx, data, sel, replicas):
+        lib = _lib.load()
+        dev = data.device
+        B, N_src, C = data.shape
+        P, M = sel.shape
+        out = torch.empty(P, M, C, dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            st = lib.dpc_select_points(P, int(replicas), N_src, M, C, _ptr(data), _ptr(sel),
+                                       _ptr(out), _stream(dev))
+        _lib.check(st, "select_points")
+        ctx.save_for_backward(sel)
+        ctx.dims = (P, int(replicas), N_src, M, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        (sel,) = ctx.saved_tensors
+        P, R, N_src, M, C = ctx.dims
+        dev = sel.device
+        g_out = _f32(g_out, "g_out", (P, M, C))
+        inv = _scratch("inv", P * N_src * 4, dev)
+        g = torch.empty(P // R, N_src, C, dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            st = lib.dpc_replica_reduce(P, R, N_src, M, C, _ptr(g_out), _ptr(sel), _ptr(inv),
+                                        _ptr(g), _stream(dev))
+        _lib.check(st, "replica_reduce")
+        return g, None, None

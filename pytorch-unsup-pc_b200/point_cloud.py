@@ -112,6 +112,114 @@ def smoothen_voxels3d(cfg, voxels, kernel):
     return out.reshape(P, 1, Vz, V, V)
 
 
+def _new_seed():
+    # one draw from torch's default CPU generator: follows torch.manual_seed, no device sync
+    return int(torch.empty((), dtype=torch.int64).random_().item())
+
+
+def _selection(indices, P, N_src, device):
+    """Validate a user-supplied dropout selection: [P,M] or the reference sampler's
+    [P,M,2] (batch index, point index) layout (point_cloud_to.py:275-283)."""
+    sel = torch.as_tensor(indices)
+    if sel.dim() == 3 and sel.shape[-1] == 2:
+        sel = sel[..., 1]
+    if sel.dim() != 2 or sel.shape[0] != P or not 1 <= sel.shape[1] <= N_src:
+        raise ValueError("indices must be [P,M] (or the reference's [P,M,2]) with P=%d and "
+                         "1 <= M <= %d, got %s" % (P, N_src, tuple(sel.shape)))
+    if sel.is_floating_point():
+        raise TypeError("indices must be an integer tensor")
+    return sel.to(device=device, dtype=torch.int32).contiguous()
+
+
+def pc_point_dropout(points, rgb, keep_prob, seed=None, indices=None):
+    """points [P,N,3] (+ rgb [P,N,C]) -> ([P,M,3], [P,M,C] or None), M = int(N * keep_prob):
+    an independent random M-subset of every cloud (point_cloud_to.py:269-295), sampled and
+    gathered on the device -- the reference samples with numpy on the host and gathers by
+    advanced indexing.  ``indices`` ([P,M] or the reference's [P,M,2]) replaces the sampler;
+    ``seed`` makes it reproducible (default: a draw from torch's generator)."""
+    pts = ops._f32(points, "points")
+    if pts.dim() != 3:
+        raise ValueError("points must be [P,N,C], got %s" % (tuple(pts.shape),))
+    P, N, _ = pts.shape
+    if indices is None:
+        M = int(N * keep_prob)
+        if not 1 <= M <= N:
+            raise ValueError("keep_prob=%r keeps %d of %d points" % (keep_prob, M, N))
+        sel = ops.dropout_indices(P, N, M, _new_seed() if seed is None else seed, pts.device)
+    else:
+        sel = _selection(indices, P, N, pts.device)
+    out = ops.SelectPointsFn.apply(pts, sel, 1)
+    out_rgb = None
+    if rgb is not None:
+        col = ops._f32(rgb, "rgb")
+        if col.dim() != 3 or col.shape[:2] != pts.shape[:2] or col.shape[2] > 4:
+            raise ValueError("rgb must be [P,N,C<=4] like points, got %s" % (tuple(col.shape),))
+        out_rgb = ops.SelectPointsFn.apply(col, sel, 1)
+    return out, out_rgb
+
+
+def pointcloud_project_replicated(cfg, point_cloud, transform, predicted_translation, all_rgb,
+                                  kernel=None, scaling_factor=None, focal_length=None,
+                                  keep_prob=1.0, indices=None, seed=None):
+    """``pointcloud_project_fast`` on the UN-replicated clouds (next row f2).
+
+    The reference materialises every predicted cloud ``step_size x num_candidates`` times
+    (tf_repeat_0, model_pc_to.py:47-56, 302-306), drops points from every copy with a host-side
+    sampler (pc_point_dropout, :254-258) and projects the copies.  Here ``point_cloud`` is the
+    decoder's [B,N,3] tensor, ``transform`` holds the P = B x replicas poses in tf_repeat_0
+    order (the replicas of a cloud adjacent) and the kernels read cloud ``b // replicas``
+    through the dropout selection: neither copy exists, and the gradient comes back already
+    summed over the replicas, [B,N,3].  Outputs are those of
+    ``pointcloud_project_fast(cfg, pc_point_dropout(tf_repeat_0(point_cloud, replicas)), ...)``
+    plus ``dropout_indices`` ([P,M] int32, or None when nothing is dropped).
+
+    ``keep_prob`` < 1 samples M = int(N * keep_prob) points per projection on the device;
+    ``indices`` ([P,M], distinct per row) supplies the selection instead."""
+    _check_quaternion_cfg(cfg)
+    if all_rgb is not None:
+        raise NotImplementedError("all_rgb: the rgb branch is broken in the reference "
+                                  "(point_cloud_to.py:64) and not part of this path")
+    if getattr(cfg, "ptn_max_projection", False):
+        raise NotImplementedError("ptn_max_projection is broken in the reference "
+                                  "(point_cloud_to.py:234,242) and not supported")
+    pts = ops._f32(point_cloud, "point_cloud")
+    if pts.dim() != 3 or pts.shape[-1] != 3:
+        raise ValueError("point_cloud must be [B,N,3], got %s" % (tuple(pts.shape),))
+    B, N_src, _ = pts.shape
+    quat = ops._f32(transform, "transform")
+    if quat.dim() != 2 or quat.shape[1] != 4 or quat.shape[0] % B != 0:
+        raise ValueError("transform must be [B*replicas,4] for %d clouds, got %s"
+                         % (B, tuple(quat.shape)))
+    P = quat.shape[0]
+    sel = None
+    if indices is not None:
+        sel = _selection(indices, P, N_src, pts.device)
+    elif keep_prob != 1:
+        M = int(N_src * keep_prob)
+        if not 1 <= M <= N_src:
+            raise ValueError("keep_prob=%r keeps %d of %d points" % (keep_prob, M, N_src))
+        sel = ops.dropout_indices(P, N_src, M, _new_seed() if seed is None else seed, pts.device)
+    N = N_src if sel is None else sel.shape[1]
+    trans = ops._f32(predicted_translation, "predicted_translation", (P, 3))
+    scale = _vec(scaling_factor, "scaling_factor", P)
+    focal = _vec(focal_length, "focal_length", P)
+    params = ops.make_params(cfg, P, N, flip_y=True)
+    mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
+        pts, quat, trans, focal, scale, params, ops.host_taps(kernel),
+        _options["voxels"], _options["drc_probs"], _scatter_mode(), _options["plane_local"],
+        (P // B, N_src, sel))
+    return {
+        "proj": mask.unsqueeze(-1),
+        "voxels": None if voxels is None else voxels.unsqueeze(-1),
+        "tr_pc": tr_pc,
+        "voxels_rgb": None,
+        "proj_rgb": None,
+        "drc_probs": None if probs is None else probs.unsqueeze(-1),
+        "proj_depth": depth.unsqueeze(-1),
+        "dropout_indices": sel,
+    }
+
+
 def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation, all_rgb,
                             kernel=None, scaling_factor=None, focal_length=None):
     """The whole projection (point_cloud_to.py:191-263): returns the reference's
