@@ -48,6 +48,23 @@
 
 namespace dpc {
 
+// A/B switches (scripts/build_variant.sh): compile-time depth specialisation of the forward /
+// backward ray kernels, resident CTAs per SM the backward's register budget is sized for
+#ifndef DPC_VZ_FWD
+#define DPC_VZ_FWD 1
+#endif
+#ifndef DPC_VZ_BWD
+#define DPC_VZ_BWD 1
+#endif
+#ifndef DPC_BWD_MINB
+#define DPC_BWD_MINB 4
+#endif
+#ifndef DPC_FWD_MINB
+#define DPC_FWD_MINB 1
+#endif
+#ifndef DPC_FWD_L10
+#define DPC_FWD_L10 28
+#endif
 constexpr int kFwdThreads = 128;   // ray pairs per CTA (forward)
 constexpr int kBwdThreads = 64;    // ray pairs per CTA (backward: shared-memory bound)
 
@@ -101,6 +118,7 @@ template <> struct RingLen<0> { static constexpr int L = 8; };
 template <> struct RingLen<5> { static constexpr int L = 16; };
 template <int R> struct FwdRingLen { static constexpr int L = RingLen<R>::L; };
 template <> struct FwdRingLen<0> { static constexpr int L = 16; };
+template <> struct FwdRingLen<10> { static constexpr int L = DPC_FWD_L10; };
 
 struct RayConst {
   int P, Vz;          // P = projections in the whole batch (probs stride)
@@ -133,7 +151,7 @@ static RayConst make_ray_const(const DrcArgs &a) {
 }
 
 #ifndef DPC_RING_NACC
-#define DPC_RING_NACC 3
+#define DPC_RING_NACC 2
 #endif
 // sum_t k[t] * ring[(first + t) % L]  (reversed: k[2R - t]), packed pairs
 template <int R, int L>
@@ -144,12 +162,11 @@ __device__ __forceinline__ u64 ring_dot2(const u64 (&ring)[L], const u64 (&k2)[2
   constexpr int NACC = W >= 12 ? DPC_RING_NACC : (W >= 3 ? 3 : 1);
   u64 acc[NACC];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0;   // bit pattern 0 == (0.f, 0.f)
-#pragma unroll
   for (int t = 0; t < W; ++t) {
     const u64 v = ring[(first + t) % L];
     const u64 k = reversed ? k2[W - 1 - t] : k2[t];
-    acc[t % NACC] = fma2(k, v, acc[t % NACC]);
+    // the first term of every chain is a plain product: no zeroed accumulator registers
+    acc[t % NACC] = t < NACC ? mul2(k, v) : fma2(k, v, acc[t % NACC]);
   }
 #pragma unroll
   for (int n = NACC; n > 1; n = (n + 1) / 2)
@@ -173,11 +190,17 @@ __device__ __forceinline__ void pair_index(const RayConst &c, int threads, int &
 // Streams the pair blurZ(col)_z, z = 0..Vz-1, to sink(j, z, pair); j is the
 // compile-time position inside the current block of L steps.  SAVE writes the
 // blurred pair back over the input column (bs may alias col).
-template <int V, int R, bool SAVE, typename Sink>
-__device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int Vz,
+// VZ > 0: the depth is a compile-time constant (== Vz).  The blocks whose loads
+// and outputs are all in range run in a rolled loop WITHOUT any range check;
+// the last block(s) are unrolled with a compile-time z0, so their checks fold
+// away.  With a runtime depth (VZ == 0) every step carries two range checks --
+// a branch per step, which also stops the scheduler from overlapping steps.
+template <int V, int R, bool SAVE, int VZ, typename Sink>
+__device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int Vz_rt,
                                                const Taps<R> &taps, Sink &&sink) {
   constexpr int W = 2 * R + 1, L = FwdRingLen<R>::L, AHEAD = R + (L - W);   // load-ahead in steps
   constexpr int VV = V * V;
+  const int Vz = VZ ? VZ : Vz_rt;
   u64 k2[W];
 #pragma unroll
   for (int t = 0; t < W; ++t) k2[t] = pack2(taps.k[t], taps.k[t]);
@@ -187,28 +210,48 @@ __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int 
 #pragma unroll
   for (int i = 0; i < AHEAD; ++i)
     if (i < Vz) ring[i] = *reinterpret_cast<const u64 *>(col + (size_t)i * VV);
-#pragma unroll 1
-  for (int z0 = 0; z0 < Vz; z0 += L) {
-#pragma unroll
-    for (int j = 0; j < L; ++j) {
-      const int z = z0 + j;
-      if (z < Vz) {
-        ring[(j + AHEAD) % L] =
-            (z + AHEAD < Vz) ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
-        const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
-        if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = b2;
-        sink(j, z, b2);
-      }
+  // one step; `checked` folds to a constant in the unrolled tail blocks
+  auto step = [&](const int j, const int z, const bool in_range, const bool load_ok) __attribute__((always_inline)) {
+    if (in_range) {
+      ring[(j + AHEAD) % L] =
+          load_ok ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
+      const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
+      if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = b2;
+      sink(j, z, b2);
     }
-    col += (size_t)L * VV;
-    if (SAVE) bs += (size_t)L * VV;
+  };
+  if (VZ) {
+    constexpr int NBLK = (VZ + L - 1) / L;
+    constexpr int NSAFE = VZ > AHEAD ? (VZ - AHEAD) / L : 0;   // (bi+1) L - 1 + AHEAD < VZ
+#pragma unroll 1
+    for (int bi = 0; bi < NSAFE; ++bi) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) step(j, bi * L + j, true, true);
+      col += (size_t)L * VV;
+      if (SAVE) bs += (size_t)L * VV;
+    }
+#pragma unroll
+    for (int bi = NSAFE; bi < NBLK; ++bi) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) step(j, bi * L + j, bi * L + j < VZ, bi * L + j + AHEAD < VZ);
+      col += (size_t)L * VV;
+      if (SAVE) bs += (size_t)L * VV;
+    }
+  } else {
+#pragma unroll 1
+    for (int z0 = 0; z0 < Vz; z0 += L) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) step(j, z0 + j, z0 + j < Vz, z0 + j + AHEAD < Vz);
+      col += (size_t)L * VV;
+      if (SAVE) bs += (size_t)L * VV;
+    }
   }
 }
 
 // EXTRA: the optional voxels / probs outputs exist.  `grid` and `bsave` may
 // alias (in-place save), so neither is __restrict__.
-template <int V, int R, bool EXTRA, bool SAVE>
-__global__ void __launch_bounds__(kFwdThreads)
+template <int V, int R, bool EXTRA, bool SAVE, int VZ>
+__global__ void __launch_bounds__(kFwdThreads, VZ ? DPC_FWD_MINB : 1)
 blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayConst c,
                      const Taps<R> kz, float *bsave, float *__restrict__ mask,
                      float *__restrict__ depth, float *__restrict__ voxels,
@@ -225,8 +268,8 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   float *vx = (EXTRA && voxels) ? voxels + col0 : nullptr;
   float *pr = (EXTRA && probs) ? probs + oi : nullptr;
   const size_t pstride = (size_t)c.P * VV;
-  stream_blur_z2<V, R, SAVE>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
-                             [&](int j, int z, u64 b2) {
+  stream_blur_z2<V, R, SAVE, VZ>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
+                                 [&](int j, int z, u64 b2) {
     const float psi = fmaf(kf, c.inv_z, c.depth0);
     kf += 1.f;
     const u64 sb2 = mul2(s2, b2);
@@ -251,8 +294,11 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   if (depth) *reinterpret_cast<u64 *>(depth + oi) = fma2(pack2(c.max_depth, c.max_depth), pz2, d2);
 }
 
-template <int V, int R, bool EXTRA>
-__global__ void __launch_bounds__(kBwdThreads)
+// VZ > 0: compile-time depth (== c.Vz), see stream_blur_z2: the blocks that lie
+// entirely inside the column run in rolled loops without range checks, the last
+// block(s) are unrolled with a compile-time z0.
+template <int V, int R, bool EXTRA, int VZ>
+__global__ void __launch_bounds__(kBwdThreads, VZ ? DPC_BWD_MINB : 1)
 drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ scale, RayConst c,
                      const Taps<R> kz, const float *__restrict__ g_mask,
                      const float *__restrict__ g_depth, const float *__restrict__ g_probs,
@@ -262,14 +308,18 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   if (zero_ints && blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kBwdThreads) zero_ints[i] = 0;
   constexpr int VV = V * V;
+  const int Vz = VZ ? VZ : c.Vz;
   extern __shared__ float2 sm2[];
   float2 *sB = sm2 + threadIdx.x;                        // [Vz][threads]    saved blurZ pair
-  float2 *sC = sm2 + c.Vz * kBwdThreads + threadIdx.x;   // [nblk][threads]  T at block starts
+  float2 *sC = sm2 + Vz * kBwdThreads + threadIdx.x;     // [nblk][threads]  T at block starts
   int b, yx, oi;
   pair_index<V>(c, kBwdThreads, b, yx, oi);
-  const size_t col0 = (size_t)b * c.Vz * VV + yx;
+  const size_t col0 = (size_t)b * Vz * VV + yx;
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
-  const int nblk = (c.Vz + L - 1) / L;
+  const int nblk = (Vz + L - 1) / L;
+  // blocks [0, n_full) lie inside the column; blocks [0, n_store) also have every output row
+  // z = k + R inside it.  Compile-time when VZ is; 0 otherwise (every step checked).
+  constexpr int NFULL = VZ / L, NSTORE = VZ > R ? (VZ - R) / L : 0, NBLK = (VZ + L - 1) / L;
 
   const u64 s2 = pack2(s, s), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
   const u64 ec2 = pack2(c.exp_clip, c.exp_clip);
@@ -284,22 +334,31 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   {
     const float *ld = bgrid + col0;
     u64 T2 = one2;
-#pragma unroll 1
-    for (int bi = 0; bi < nblk; ++bi) {
+    // block bi; `full`: every step is inside the column
+    auto stage_block = [&](const int bi, const bool full) __attribute__((always_inline)) {
       sC2[bi * kBwdThreads] = T2;
       u64 vals[L];
 #pragma unroll
       for (int j = 0; j < L; ++j)
-        vals[j] = (bi * L + j < c.Vz) ? __ldg(reinterpret_cast<const u64 *>(ld + (size_t)j * VV)) : 0ull;
+        vals[j] = (full || bi * L + j < Vz) ? __ldg(reinterpret_cast<const u64 *>(ld + (size_t)j * VV)) : 0ull;
       ld += (size_t)L * VV;
 #pragma unroll
       for (int j = 0; j < L; ++j) {
         const int z = bi * L + j;
-        if (z < c.Vz) {
+        if (full || z < Vz) {
           sB2[z * kBwdThreads] = vals[j];
           T2 = mul2(T2, one_minus_v(vals[j]));
         }
       }
+    };
+    if (VZ) {
+#pragma unroll 1
+      for (int bi = 0; bi < NFULL; ++bi) stage_block(bi, true);
+#pragma unroll
+      for (int bi = NFULL; bi < NBLK; ++bi) stage_block(bi, false);
+    } else {
+#pragma unroll 1
+      for (int bi = 0; bi < nblk; ++bi) stage_block(bi, false);
     }
   }
   // ---- sweep 2: reverse scan + Z-blur adjoint ----
@@ -308,7 +367,7 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   const size_t pstride = (size_t)c.P * VV;
   u64 D2 = pack2(c.max_depth * gd.x, c.max_depth * gd.y);
   if (EXTRA && g_probs)
-    D2 = add2(D2, __ldg(reinterpret_cast<const u64 *>(g_probs + (size_t)c.Vz * pstride + oi)));
+    D2 = add2(D2, __ldg(reinterpret_cast<const u64 *>(g_probs + (size_t)Vz * pstride + oi)));
   D2 = mul2(D2, ec2);
   u64 ds2 = 0;
   u64 k2[W];
@@ -318,8 +377,8 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
 #pragma unroll
   for (int i = 0; i < L; ++i) ring[i] = 0;
 
-#pragma unroll 1
-  for (int bi = nblk - 1; bi >= 0; --bi) {
+  // block bi in reverse; `full`: every step inside the column, `store_all`: every output row too
+  auto reverse_block = [&](const int bi, const bool full, const bool store_all) __attribute__((always_inline)) {
     const int z0 = bi * L;
     // re-expand T_k inside the block from its checkpoint
     u64 tseg[L];
@@ -328,7 +387,7 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
 #pragma unroll
       for (int j = 0; j < L; ++j) {
         tseg[j] = T2;
-        if (z0 + j < c.Vz) T2 = mul2(T2, one_minus_v(sB2[(z0 + j) * kBwdThreads]));
+        if (full || z0 + j < Vz) T2 = mul2(T2, one_minus_v(sB2[(z0 + j) * kBwdThreads]));
       }
     }
     // block-base pointers; inside the block every offset is an immediate
@@ -340,7 +399,7 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
     for (int j = L - 1; j >= 0; --j) {
       const int k = z0 + j;
       u64 gB2 = 0;
-      if (k < c.Vz) {
+      if (full || k < Vz) {
         const u64 b2 = sB2[k * kBwdThreads];
         const u64 sb2 = mul2(s2, b2);
         const float psi = fmaf(kf0 + (float)j, c.inv_z, c.depth0);
@@ -366,9 +425,18 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
       ring[j] = gB2;
       // out[z] = sum_t kz[2R-t] * in[k + t], z = k + R   (adjoint = reversed taps);
       // in[k + t] sits in slot (j + t) % L
-      if (k + R < c.Vz)
+      if (store_all || k + R < Vz)
         *reinterpret_cast<u64 *>(gout + (size_t)j * VV) = ring_dot2<R, L>(ring, k2, j, true);
     }
+  };
+  if (VZ) {
+#pragma unroll
+    for (int bi = NBLK - 1; bi >= NSTORE; --bi) reverse_block(bi, bi < NFULL, false);
+#pragma unroll 1
+    for (int bi = NSTORE - 1; bi >= 0; --bi) reverse_block(bi, true, true);
+  } else {
+#pragma unroll 1
+    for (int bi = nblk - 1; bi >= 0; --bi) reverse_block(bi, false, false);
   }
   if (R > 0) {
     // flush: inputs k = -1 .. -R are zero; they complete the outputs z = R-1 .. 0
@@ -377,7 +445,7 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
     for (int j = L - 1; j >= L - R; --j) {
       ring[j] = 0;
       const int z = j - L + R;
-      if (z < c.Vz) *reinterpret_cast<u64 *>(gout + (size_t)z * VV) = ring_dot2<R, L>(ring, k2, j, true);
+      if (z < Vz) *reinterpret_cast<u64 *>(gout + (size_t)z * VV) = ring_dot2<R, L>(ring, k2, j, true);
     }
   }
   // ---- dL/dscale: fixed-order block reduction ----
@@ -406,7 +474,7 @@ blur_z_kernel(const float *src, float *dst, int Vz, const Taps<R> kz) {
   const int pair = blockIdx.x * kFwdThreads + threadIdx.x;
   const int b = pair / (VV / 2), yx = 2 * (pair - b * (VV / 2));
   const size_t col0 = (size_t)b * Vz * VV + yx;
-  stream_blur_z2<V, R, true>(src + col0, dst + col0, Vz, kz, [](int, int, u64) {});
+  stream_blur_z2<V, R, true, 0>(src + col0, dst + col0, Vz, kz, [](int, int, u64) {});
 }
 
 __global__ void __launch_bounds__(128)
@@ -463,11 +531,13 @@ static void launch_fwd_vr(const DrcArgs &a, const RayConst &c, const Taps<R> &ta
                           float *mask, float *depth, float *voxels, float *probs, cudaStream_t s) {
   const int blocks = a.P * (V * V / 2) / kFwdThreads;
   const bool extra = voxels || probs;
-#define DPC_FWD(EX, SV)                                                                 \
-  blurz_drc_fwd_kernel<V, R, EX, SV><<<blocks, kFwdThreads, 0, s>>>(a.grid, a.scale, c, taps, \
-                                                                    bsave, mask, depth, voxels, probs)
-  if (bsave) { if (extra) DPC_FWD(true, true); else DPC_FWD(false, true); }
-  else { if (extra) DPC_FWD(true, false); else DPC_FWD(false, false); }
+#define DPC_FWD(EX, SV, VZ)                                                                 \
+  blurz_drc_fwd_kernel<V, R, EX, SV, VZ><<<blocks, kFwdThreads, 0, s>>>(a.grid, a.scale, c, taps, \
+                                                                        bsave, mask, depth, voxels, probs)
+  // the training configuration (cubic grid, no optional outputs, saved B) gets the
+  // kernel with the depth as a compile-time constant
+  if (bsave) { if (extra) DPC_FWD(true, true, 0); else if (DPC_VZ_FWD && a.Vz == V) DPC_FWD(false, true, V); else DPC_FWD(false, true, 0); }
+  else { if (extra) DPC_FWD(true, false, 0); else DPC_FWD(false, false, 0); }
 #undef DPC_FWD
 }
 
@@ -480,8 +550,8 @@ int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave
   return check_launch("blurz_drc_fwd");
 }
 
-template <int V, int R, bool EXTRA>
-static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
+template <int V, int R, bool EXTRA, int VZ>
+static void launch_bwd_vz(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
                            const float *g_mask, const float *g_depth, const float *g_probs,
                            const float *g_voxels, float *g_grid, float *scale_partials,
                            int *zero_ints, int n_zero, cudaStream_t s) {
@@ -490,14 +560,29 @@ static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &t
   const size_t smem = (size_t)(a.Vz + nblk) * kBwdThreads * sizeof(float2);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(drc_blurz_bwd_kernel<V, R, EXTRA>,
+    cudaFuncSetAttribute(drc_blurz_bwd_kernel<V, R, EXTRA, VZ>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;
   }
   const int blocks = a.P * (V * V / 2) / kBwdThreads;
-  drc_blurz_bwd_kernel<V, R, EXTRA><<<blocks, kBwdThreads, smem, s>>>(
+  drc_blurz_bwd_kernel<V, R, EXTRA, VZ><<<blocks, kBwdThreads, smem, s>>>(
       a.grid, a.scale, c, taps, g_mask, g_depth, g_probs, g_voxels, g_grid,
       a.scale ? scale_partials : nullptr, zero_ints, n_zero);
+}
+
+template <int V, int R, bool EXTRA>
+static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
+                           const float *g_mask, const float *g_depth, const float *g_probs,
+                           const float *g_voxels, float *g_grid, float *scale_partials,
+                           int *zero_ints, int n_zero, cudaStream_t s) {
+  // the training configuration (cubic grid, gradients through mask/depth only) gets the
+  // kernel with the depth as a compile-time constant
+  if (DPC_VZ_BWD && !EXTRA && a.Vz == V)
+    launch_bwd_vz<V, R, false, V>(a, c, taps, g_mask, g_depth, nullptr, nullptr, g_grid,
+                                  scale_partials, zero_ints, n_zero, s);
+  else
+    launch_bwd_vz<V, R, EXTRA, 0>(a, c, taps, g_mask, g_depth, g_probs, g_voxels, g_grid,
+                                  scale_partials, zero_ints, n_zero, s);
 }
 
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
