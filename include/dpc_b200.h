@@ -42,7 +42,7 @@ extern "C" {
 #define DPC_API
 #endif
 
-#define DPC_B200_VERSION 120
+#define DPC_B200_VERSION 130
 #define DPC_MAX_TAPS 21
 
 typedef enum {
@@ -62,7 +62,13 @@ typedef struct {
   double drc_clip;          /* cfg.drc_logsum_clip_val                          */
   int32_t drc_logsum;       /* cfg.drc_logsum: 1 = clip + exp(clip) end factors */
   int32_t flip_y;           /* 1 = apply the Y flips of point_cloud_to.py:239,242 */
+  int32_t outputs;          /* DPC_OUT_* flags: the optional outputs dpc_project_fwd
+                               materialises; dpc_project_bwd must get the same value
+                               (it selects the layout of the saved ray state)        */
 } dpc_params;
+
+#define DPC_OUT_VOXELS 1    /* "voxels"    [P,Vz,V,V]   (point_cloud_to.py:222) */
+#define DPC_OUT_PROBS 2     /* "drc_probs" [Vz+1,P,V,V] (point_cloud_to.py:239) */
 
 /* Flags for dpc_project_fwd / scatter mode. */
 #define DPC_SCATTER_ATOMIC 0
@@ -75,8 +81,10 @@ DPC_API const char *dpc_last_error(void);
  * shared by all of them; 256-byte aligned). */
 DPC_API size_t dpc_workspace_bytes(const dpc_params *p);
 
-/* Bytes of the per-point cell records dpc_project_fwd saves for dpc_project_bwd
- * (z cell byte + {iy,ix,rz,ry,rx} per point; about 17 bytes per point). */
+/* Bytes of the state besides grid_b / clamp_bits that dpc_project_fwd saves for
+ * dpc_project_bwd: the per-point cell records (z cell byte + two 16-byte
+ * records per point) and the ray-transmittance checkpoints of the DRC kernels
+ * (Vz/8 V x V planes per projection). */
 DPC_API size_t dpc_cells_bytes(const dpc_params *p);
 
 /* ---- a1+a2: quaternion.py:110-132 quaternion_rotate +
@@ -123,8 +131,11 @@ DPC_API int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, 
 /* ---- a12+a13: point_cloud_to.py:191-263 pointcloud_project_fast ----------
  * The whole path in one call: pose -> scatter -> clamp -> blur XY (in place)
  * -> blur Z (in place) + scale + clip + DRC ray march (+ Y flips).
- * Saved for backward: grid_b [P,Vz,V,V] (the blurred occupancy B, before
- * scaling), clamp_bits (raw <= 1 mask) and cells (dpc_cells_bytes; NULL ok).
+ * Saved for backward (opaque to the caller): grid_b [P,Vz,V,V] (the blurred
+ * occupancy B before scaling; or, on the plane-local path with a cubic grid, no
+ * optional outputs and drc_logsum, the clipped ray occupancy v = clip(s B) with
+ * the clamp gate in its sign bit), clamp_bits (raw <= 1 mask) and cells
+ * (dpc_cells_bytes; NULL ok).
  * With cells != NULL and DPC_SCATTER_ATOMIC the plane-local path runs: the raw
  * grid never exists in global memory -- a pose kernel writes the cell records
  * and every Z-plane is built in shared memory by the blur kernel from the

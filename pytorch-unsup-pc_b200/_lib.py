@@ -18,6 +18,8 @@ c_size_t = ctypes.c_size_t
 
 SCATTER_ATOMIC = 0
 SCATTER_SORTED = 1
+OUT_VOXELS = 1      # dpc_params.outputs flags
+OUT_PROBS = 2
 MAX_TAPS = 21
 
 
@@ -27,7 +29,8 @@ class Params(ctypes.Structure):
                 ("Vz", ctypes.c_int32), ("V", ctypes.c_int32),
                 ("camera_distance", ctypes.c_double), ("focal_length", ctypes.c_double),
                 ("max_depth", ctypes.c_double), ("drc_clip", ctypes.c_double),
-                ("drc_logsum", ctypes.c_int32), ("flip_y", ctypes.c_int32)]
+                ("drc_logsum", ctypes.c_int32), ("flip_y", ctypes.c_int32),
+                ("outputs", ctypes.c_int32)]
 
 
 _P = ctypes.POINTER(Params)

@@ -172,7 +172,7 @@ int dpc_version(void) { return DPC_B200_VERSION; }
 
 size_t dpc_cells_bytes(const dpc_params *p) {
   if (!p || p->P < 1 || p->N < 1) return 0;
-  return cells_bytes(p->P, p->N, p->Vz);
+  return ray_ck_offset(p->P, p->N, p->Vz) + ray_ck_bytes(p->P, p->Vz, p->V);
 }
 const char *dpc_last_error(void) { return g_err; }
 
@@ -276,15 +276,13 @@ int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, float *g
                                      (cudaStream_t)stream);
 }
 
-// ---- optional chunked two-stream pipeline (experiment, off by default) -------
-// Idea: run the batch as chunks of `chunk` projections on two internal streams
-// so that one chunk's kernels overlap the other's and a chunk's grid stays in
-// the 126 MB L2 between the kernel that writes it and the kernels that read it.
-// Measured on B200 at P=64, 64^3 (CUDA-graph replay, so no host launch cost):
-// 1 chunk 218 us/step, 2 chunks 223, 4 chunks 264, 8 chunks 333 -- the smaller
-// grids lose more to wave quantisation and per-kernel ramp than they gain, so
-// the default is ONE pass over the whole batch on the caller's stream.
-// DPC_CHUNK=<n> (env) re-enables chunking for experiments.
+// ---- two-stream half-batch pipeline -------------------------------------------
+// The batch runs as chunks of projections on two internal streams, so one chunk's kernels overlap
+// the other's.  History (B200, P=64, 64^3, CUDA-graph replay): with the first kernels chunking
+// lost (1 chunk 218 us/step, 2 chunks 223, 4 chunks 264, 8 chunks 333: wave quantisation and
+// per-kernel ramp); with the current grid kernels the latency-bound point kernels are a quarter
+// of the step and two half-batches win (148.0 vs 153.6 us), so that is the default for P >= 64.
+// DPC_CHUNK=<n> (env) sets the chunk size (n >= P: one pass on the caller's stream).
 struct Pipeline {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
@@ -316,6 +314,11 @@ static int chunk_size(const dpc_params *p) {
     env_chunk = e ? atoi(e) : 0;
   }
   if (env_chunk > 0) return env_chunk;
+  // Two half-batches on two internal streams: the latency-bound point kernels (pose, binning,
+  // pose adjoint: ~25 % of the step, a few hundred CTAs each) of one half overlap the FMA-bound
+  // grid kernels of the other.  Measured at workload A: 148.0 vs 153.6 us per step; quarters
+  // lose (177.5 us: too few CTAs per kernel).
+  if (p->P >= 64 && p->P % 2 == 0) return p->P / 2;
   return p->P;
 }
 
@@ -329,6 +332,17 @@ struct FwdPtrs {
 // The plane-local path packs (n, iy, ix) into 32 bits and bins by a z-cell byte.
 static bool plane_local_ok(const dpc_params *p) {
   return p->N <= 65535 && p->V <= 256 && p->Vz <= 192;
+}
+
+// The DRC kernels' fast saved state (drc.cu): decided from what BOTH passes know.
+static bool fast_ray_state(const dpc_params *p, const void *cells, int scatter_mode) {
+  return cells && scatter_mode == DPC_SCATTER_ATOMIC && p->Vz == p->V && p->outputs == 0 &&
+         p->drc_logsum != 0;
+}
+static void set_ray_state(DrcArgs &da, const dpc_params *p, void *cells, int b0) {
+  da.ck_slots = ray_ck_slots(p->Vz);
+  da.tck = (float *)((char *)cells + ray_ck_offset(p->P, p->N, p->Vz)) +
+           (size_t)b0 * da.ck_slots * p->V * p->V;
 }
 
 // the records of projections [b0, b0 + n) inside a whole-batch cells buffer
@@ -383,6 +397,7 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   // blur Z + scale + clip + DRC; the blurred occupancy overwrites grid in place (saved for bwd)
   DrcArgs da = drc_args(&sp, grid, q.scale ? q.scale + b0 : nullptr);
   da.P_total = p->P;
+  if (fast_ray_state(p, q.cells, scatter_mode)) set_ray_state(da, p, q.cells, b0);
   DPC_TRY(launch_blurz_drc_fwd(da, tz, kz, grid, q.mask + b0 * I, q.depth ? q.depth + b0 * I : nullptr,
                                q.voxels ? q.voxels + b0 * G : nullptr,
                                q.probs ? q.probs + b0 * I : nullptr, s));
@@ -400,6 +415,11 @@ static int project_fwd_impl(const dpc_params *p, const Replica &rep, const float
   DPC_TRY(check_params(p, true));
   DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
   DPC_REQUIRE(mask);
+  if ((voxels != nullptr) != ((p->outputs & DPC_OUT_VOXELS) != 0) ||
+      (probs != nullptr) != ((p->outputs & DPC_OUT_PROBS) != 0)) {
+    set_error("project_fwd: params.outputs=%d does not match the voxels / probs pointers", p->outputs);
+    return DPC_ERR_ARG;
+  }
   if (scatter_mode == DPC_SCATTER_SORTED) cells = nullptr;   // the sorted scatter builds the grid itself
   if (!plane_local_ok(p)) cells = nullptr;
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
@@ -466,6 +486,7 @@ struct BwdPtrs {
   float *g_grid, *g_points, *g_quat, *g_trans, *g_focal, *g_scale;
   void *cells;
   Replica rep;
+  void *fast_rays = nullptr;   // the cells buffer when the forward saved the fast ray state
 };
 
 static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &q, const float *tx,
@@ -480,6 +501,7 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
   float *g_grid = q.g_grid + b0 * G;
   DrcArgs da = drc_args(&sp, q.grid_b + b0 * G, q.scale ? q.scale + b0 : nullptr);
   da.P_total = p->P;
+  if (q.fast_rays) set_ray_state(da, p, q.fast_rays, b0);
   stage_mark(s);
   DPC_TRY(launch_drc_blurz_bwd(da, tz, kz, q.g_mask ? q.g_mask + b0 * I : nullptr,
                                q.g_depth ? q.g_depth + b0 * I : nullptr,
@@ -550,10 +572,19 @@ static int project_bwd_impl(const dpc_params *p, const Replica &rep, const float
   // The plane gather pays off while several CTAs share an SM (V <= 64); a 128^2
   // plane takes the whole SM's shared memory and its gather runs with nothing to
   // overlap it (measured at workload B: 1269 vs 773 us), so 128^3 gathers from the grid.
+  void *fast_rays = nullptr;
+  if (plane_local_ok(p) && fast_ray_state(p, cells, DPC_SCATTER_ATOMIC)) {
+    if (g_probs || g_voxels) {
+      set_error("project_bwd: g_probs / g_voxels given but params.outputs says the forward did "
+                "not materialise them");
+      return DPC_ERR_ARG;
+    }
+    fast_rays = const_cast<void *>(cells);
+  }
   if (!plane_local_ok(p) || p->V > 64) cells = nullptr;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
                   g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
-                  const_cast<void *>(cells), rep};
+                  const_cast<void *>(cells), rep, fast_rays};
   const int chunk = rep.replicas > 0 ? p->P : chunk_size(p);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   int rc = DPC_OK;

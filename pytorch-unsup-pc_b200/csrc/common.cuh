@@ -95,6 +95,12 @@ inline size_t cells_bytes(int P, int N, int Vz) {
   return cells_z_bytes(P, N) + (size_t)P * N * 2 * sizeof(uint4) +
          (size_t)P * cells_zstride(Vz) * sizeof(uint32_t);
 }
+// Ray-transmittance checkpoints of the fast DRC path (drc.cu), stored behind the cell records:
+// tck [P][slots][V*V] fp32, slot i = T at the start of ray block i + 1.  The block length depends
+// on the tap radius (>= 8 steps), so Vz/8 slots always suffice.
+inline int ray_ck_slots(int Vz) { return (Vz + 7) / 8; }
+inline size_t ray_ck_offset(int P, int N, int Vz) { return (cells_bytes(P, N, Vz) + 255) & ~(size_t)255; }
+inline size_t ray_ck_bytes(int P, int Vz, int V) { return (size_t)P * ray_ck_slots(Vz) * V * V * sizeof(float); }
 inline CellsView cells_view(void *base, int P, int N, int Vz) {
   CellsView v;
   v.cellz = (uint8_t *)base;
@@ -172,6 +178,11 @@ struct DrcArgs {
   int P_total;             // projections in the whole batch (stride of the probs tensor)
   float cam_dist, max_depth, clip;
   int logsum, flip_y;
+  // fast ray state (cubic grid, no optional outputs, drc_logsum): the forward saves the clipped
+  // occupancy v with the clamp gate in its sign bit instead of B, and the transmittance at the
+  // start of every ray block in tck [P][ck_slots][V*V]; NULL = the general layout (B saved)
+  float *tck = nullptr;
+  int ck_slots = 0;
 };
 // bsave (NULL ok, may alias a.grid): receives blurZ(grid), the tensor the backward needs
 int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave, float *mask,

@@ -216,8 +216,8 @@ __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int 
       ring[(j + AHEAD) % L] =
           load_ok ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
       const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
-      if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = b2;
-      sink(j, z, b2);
+      const u64 keep2 = sink(j, z, b2);      // what the backward wants to find in this voxel pair
+      if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = keep2;
     }
   };
   if (VZ) {
@@ -250,12 +250,18 @@ __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int 
 
 // EXTRA: the optional voxels / probs outputs exist.  `grid` and `bsave` may
 // alias (in-place save), so neither is __restrict__.
-template <int V, int R, bool EXTRA, bool SAVE, int VZ>
+// FAST (needs VZ, SAVE, !EXTRA, log-sum DRC): instead of B the kernel saves what the backward
+// actually consumes -- v = clip(s B) with the sign bit set where the clip changed the value
+// (v >= clip_val > 0, so the sign is free; the gate of torch's clamp backward is "unchanged") --
+// and the transmittance T at the start of every block of L steps (tck), so that the backward
+// needs neither a forward sweep nor any clamp arithmetic.
+template <int V, int R, bool EXTRA, bool SAVE, int VZ, bool FAST>
 __global__ void __launch_bounds__(kFwdThreads, VZ ? DPC_FWD_MINB : 1)
 blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayConst c,
                      const Taps<R> kz, float *bsave, float *__restrict__ mask,
                      float *__restrict__ depth, float *__restrict__ voxels,
-                     float *__restrict__ probs) {
+                     float *__restrict__ probs, float *__restrict__ tck, int ck_slots) {
+  static_assert(!FAST || (VZ > 0 && SAVE && !EXTRA), "fast ray state: compile-time depth, saved, no extras");
   constexpr int VV = V * V;
   int b, yx, oi;
   pair_index<V>(c, kFwdThreads, b, yx, oi);
@@ -268,8 +274,13 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   float *vx = (EXTRA && voxels) ? voxels + col0 : nullptr;
   float *pr = (EXTRA && probs) ? probs + oi : nullptr;
   const size_t pstride = (size_t)c.P * VV;
+  u64 *ckp = FAST ? reinterpret_cast<u64 *>(tck + (size_t)b * ck_slots * VV + yx) : nullptr;
   stream_blur_z2<V, R, SAVE, VZ>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
-                                 [&](int j, int z, u64 b2) {
+                                 [&](int j, int z, u64 b2) -> u64 {
+    if (FAST && j == 0 && z > 0) {   // block start: checkpoint the transmittance
+      *ckp = T2;
+      ckp += VV / 2;
+    }
     const float psi = fmaf(kf, c.inv_z, c.depth0);
     kf += 1.f;
     const u64 sb2 = mul2(s2, b2);
@@ -287,6 +298,13 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
     d2 = fma2(pack2(psi, psi), p2, d2);
     T2 = mul2(T2, fma2(v2, neg2, one2));         // T *= (1 - v)
     if (EXTRA && pr) { *reinterpret_cast<u64 *>(pr) = p2; pr += pstride; }
+    if (FAST) {
+      float v0, v1, x0, x1;
+      unpack2(v2, v0, v1);
+      unpack2(sb2, x0, x1);
+      return pack2(v0 == x0 ? v0 : -v0, v1 == x1 ? v1 : -v1);
+    }
+    return b2;
   });
   const u64 pz2 = mul2(ec2, T2);
   if (EXTRA && pr) *reinterpret_cast<u64 *>(pr) = pz2;
@@ -467,6 +485,184 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
   }
 }
 
+// ---- bulk asynchronous copy (TMA engine, no tensor map: rows are contiguous) + mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Backward on the fast ray state (see blurz_drc_fwd_kernel<FAST>): one sweep.
+// The CTA's tile of the saved grid -- 64 ray pairs x VZ planes, every plane row 512
+// contiguous bytes -- is brought to shared memory by the bulk-copy engine
+// (cp.async.bulk, one instruction per row issued by warp 0, completion counted
+// on one mbarrier per ray block, deepest block first): no thread spends an
+// instruction or a register on the staging, the whole tile is in flight at once,
+// and the reverse scan starts on the deepest block while the rest is landing.
+// T at the block starts comes from the forward's checkpoints; |v| and the gate
+// come straight from the saved value, so the scan has no clamp arithmetic;
+// dL/dscale uses B = v / s on the open gates (the only voxels that count).
+template <int V, int R>
+__global__ void __launch_bounds__(kBwdThreads, DPC_BWD_MINB)
+drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restrict__ tck,
+                          int ck_slots, const float *__restrict__ scale, RayConst c,
+                          const Taps<R> kz, const float *__restrict__ g_mask,
+                          const float *__restrict__ g_depth, float *__restrict__ g_grid,
+                          float *__restrict__ scale_partials, int *__restrict__ zero_ints,
+                          int n_zero) {
+  constexpr int VZ = V, W = 2 * R + 1, L = FwdRingLen<R>::L, VV = V * V;
+  constexpr int NBLK = (VZ + L - 1) / L, NFULL = VZ / L, NSTORE = VZ > R ? (VZ - R) / L : 0;
+  constexpr uint32_t ROW_BYTES = kBwdThreads * sizeof(u64);
+  if (zero_ints && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += kBwdThreads) zero_ints[i] = 0;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  u64 *tile = reinterpret_cast<u64 *>(smraw);                              // [VZ][threads]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + (size_t)VZ * ROW_BYTES);   // [NBLK]
+  const int tid = threadIdx.x;
+  int b, yx, oi;
+  pair_index<V>(c, kBwdThreads, b, yx, oi);
+  const size_t col0 = (size_t)b * VZ * VV + yx;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NBLK; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i)
+        mbar_expect_tx(bars + i, (uint32_t)((i < NFULL ? L : VZ - NFULL * L) * ROW_BYTES));
+    }
+    __syncwarp();
+    // rows issued by the 32 lanes of warp 0, deepest rows first (measured: 35.2 us; all 64 rows
+    // from one thread: 37.7 us -- the last rows are issued too late)
+    const float *row0 = vgrid + (col0 - (size_t)(2 * tid));     // the CTA's first pair (tid == lane here)
+    for (int z = VZ - 1 - tid; z >= 0; z -= 32)
+      bulk_g2s(tile + (size_t)z * kBwdThreads, row0 + (size_t)z * VV, ROW_BYTES, bars + z / L);
+  }
+  const float s = c.has_scale ? __ldg(scale + b) : 1.f;
+  const u64 s2 = pack2(s, s), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
+  const u64 ec2 = pack2(c.exp_clip, c.exp_clip);
+  // transmittance at the block starts (block 0 starts at 1)
+  u64 tstart[NBLK];
+  tstart[0] = one2;
+#pragma unroll
+  for (int i = 1; i < NBLK; ++i)
+    tstart[i] = __ldg(reinterpret_cast<const u64 *>(tck + ((size_t)b * ck_slots + (i - 1)) * VV + yx));
+  const float2 gm = g_mask ? __ldg(reinterpret_cast<const float2 *>(g_mask + oi)) : make_float2(0.f, 0.f);
+  const float2 gd = g_depth ? __ldg(reinterpret_cast<const float2 *>(g_depth + oi)) : make_float2(0.f, 0.f);
+  u64 D2 = mul2(pack2(c.max_depth * gd.x, c.max_depth * gd.y), ec2);
+  u64 ds2 = 0;
+  u64 k2[W];
+#pragma unroll
+  for (int t = 0; t < W; ++t) k2[t] = pack2(kz.k[t], kz.k[t]);
+  u64 ring[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) ring[i] = 0;
+  const u64 *col = tile + tid;
+  auto abs2 = [](u64 w) -> u64 {
+    float a, b;
+    unpack2(w, a, b);
+    return pack2(fabsf(a), fabsf(b));
+  };
+
+  auto reverse_block = [&](const int bi, const u64 T0, const bool full, const bool store_all)
+                           __attribute__((always_inline)) {
+    const int z0 = bi * L;
+    mbar_wait(bars + bi, 0);
+    u64 tseg[L];
+    {
+      u64 T2 = T0;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        tseg[j] = T2;
+        if (full || z0 + j < VZ) T2 = mul2(T2, fma2(abs2(col[(z0 + j) * kBwdThreads]), neg2, one2));
+      }
+    }
+    float *gout = g_grid + col0 + (size_t)(z0 + R) * VV;               // row z = k + R at j = 0
+    const float kf0 = (float)z0;
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) {
+      const int k = z0 + j;
+      u64 gB2 = 0;
+      if (full || k < VZ) {
+        const u64 w2 = col[k * kBwdThreads];
+        const u64 v2 = abs2(w2);
+        const float psi = fmaf(kf0 + (float)j, c.inv_z, c.depth0);
+        u64 a2 = pack2(fmaf(psi, gd.x, gm.x), fmaf(psi, gd.y, gm.y));
+        if (j == 0 && k == 0) a2 = mul2(a2, ec2);
+        float x0, x1, w0, w1;
+        unpack2(mul2(tseg[j], fma2(D2, neg2, a2)), x0, x1);            // T (a - D)
+        unpack2(w2, w0, w1);
+        const u64 gv2 = pack2(w0 > 0.f ? x0 : 0.f, w1 > 0.f ? x1 : 0.f);   // sign bit = gate closed
+        D2 = fma2(a2, v2, mul2(fma2(v2, neg2, one2), D2));             // D = a v + (1 - v) D
+        ds2 = fma2(gv2, v2, ds2);
+        gB2 = mul2(gv2, s2);
+      }
+      ring[j] = gB2;
+      if (store_all || k + R < VZ)
+        *reinterpret_cast<u64 *>(gout + (size_t)j * VV) = ring_dot2<R, L>(ring, k2, j, true);
+    }
+  };
+#pragma unroll
+  for (int bi = NBLK - 1; bi >= NSTORE; --bi) reverse_block(bi, tstart[bi], bi < NFULL, false);
+  if (NSTORE > 0) {
+    // the remaining blocks are all alike: a rolled loop (tstart is indexed at run time only here)
+#pragma unroll 1
+    for (int bi = NSTORE - 1; bi >= 0; --bi) {
+      u64 T0 = one2;
+#pragma unroll
+      for (int i = 1; i < NSTORE; ++i) T0 = (i == bi) ? tstart[i] : T0;
+      reverse_block(bi, T0, true, true);
+    }
+  }
+  if (R > 0) {
+    // flush: inputs k = -1 .. -R are zero; they complete the outputs z = R-1 .. 0
+    float *gout = g_grid + col0;
+#pragma unroll
+    for (int j = L - 1; j >= L - R; --j) {
+      ring[j] = 0;
+      const int z = j - L + R;
+      if (z < VZ) *reinterpret_cast<u64 *>(gout + (size_t)z * VV) = ring_dot2<R, L>(ring, k2, j, true);
+    }
+  }
+  if (scale_partials) {
+    __shared__ float red[kBwdThreads / 32];
+    float ds, ds_hi;
+    unpack2(ds2, ds, ds_hi);
+    ds += ds_hi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ds += __shfl_down_sync(0xffffffffu, ds, o);
+    if ((tid & 31) == 0) red[tid >> 5] = ds;
+    __syncthreads();
+    if (tid == 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBwdThreads / 32; ++w) v += red[w];
+      // sum gv * B with B = v / s on the open gates (s == 0 closes every gate: the sum is 0)
+      scale_partials[blockIdx.x] = s != 0.f ? v / s : 0.f;
+    }
+  }
+}
+
 template <int V, int R>
 __global__ void __launch_bounds__(kFwdThreads)
 blur_z_kernel(const float *src, float *dst, int Vz, const Taps<R> kz) {
@@ -474,7 +670,7 @@ blur_z_kernel(const float *src, float *dst, int Vz, const Taps<R> kz) {
   const int pair = blockIdx.x * kFwdThreads + threadIdx.x;
   const int b = pair / (VV / 2), yx = 2 * (pair - b * (VV / 2));
   const size_t col0 = (size_t)b * Vz * VV + yx;
-  stream_blur_z2<V, R, true, 0>(src + col0, dst + col0, Vz, kz, [](int, int, u64) {});
+  stream_blur_z2<V, R, true, 0>(src + col0, dst + col0, Vz, kz, [](int, int, u64 b2) { return b2; });
 }
 
 __global__ void __launch_bounds__(128)
@@ -531,13 +727,20 @@ static void launch_fwd_vr(const DrcArgs &a, const RayConst &c, const Taps<R> &ta
                           float *mask, float *depth, float *voxels, float *probs, cudaStream_t s) {
   const int blocks = a.P * (V * V / 2) / kFwdThreads;
   const bool extra = voxels || probs;
-#define DPC_FWD(EX, SV, VZ)                                                                 \
-  blurz_drc_fwd_kernel<V, R, EX, SV, VZ><<<blocks, kFwdThreads, 0, s>>>(a.grid, a.scale, c, taps, \
-                                                                        bsave, mask, depth, voxels, probs)
-  // the training configuration (cubic grid, no optional outputs, saved B) gets the
+#define DPC_FWD(EX, SV, VZ, FS)                                                             \
+  blurz_drc_fwd_kernel<V, R, EX, SV, VZ, FS><<<blocks, kFwdThreads, 0, s>>>(                   \
+      a.grid, a.scale, c, taps, bsave, mask, depth, voxels, probs, a.tck, a.ck_slots)
+  // the training configuration (cubic grid, no optional outputs, saved state) gets the
   // kernel with the depth as a compile-time constant
-  if (bsave) { if (extra) DPC_FWD(true, true, 0); else if (DPC_VZ_FWD && a.Vz == V) DPC_FWD(false, true, V); else DPC_FWD(false, true, 0); }
-  else { if (extra) DPC_FWD(true, false, 0); else DPC_FWD(false, false, 0); }
+  // (a.tck: api.cu fast_ray_state() has checked cubic grid, log-sum DRC, no optional outputs)
+  if (bsave) {
+    if (extra) DPC_FWD(true, true, 0, false);
+    else if (a.tck && a.Vz == V) DPC_FWD(false, true, V, true);
+    else if (DPC_VZ_FWD && a.Vz == V) DPC_FWD(false, true, V, false);
+    else DPC_FWD(false, true, 0, false);
+  } else {
+    if (extra) DPC_FWD(true, false, 0, false); else DPC_FWD(false, false, 0, false);
+  }
 #undef DPC_FWD
 }
 
@@ -585,12 +788,40 @@ static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &t
                                   scale_partials, zero_ints, n_zero, s);
 }
 
+template <int V, int R>
+static void launch_bwd_fast(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
+                            const float *g_mask, const float *g_depth, float *g_grid,
+                            float *scale_partials, int *zero_ints, int n_zero, cudaStream_t s) {
+  constexpr int L = FwdRingLen<R>::L, NBLK = (V + L - 1) / L;
+  const size_t smem = (size_t)V * kBwdThreads * sizeof(u64) + NBLK * sizeof(uint64_t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(drc_blurz_bwd_fast_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    attr_done = true;
+  }
+  const int blocks = a.P * (V * V / 2) / kBwdThreads;
+  drc_blurz_bwd_fast_kernel<V, R><<<blocks, kBwdThreads, smem, s>>>(
+      a.grid, a.tck, a.ck_slots, a.scale, c, taps, g_mask, g_depth, g_grid,
+      a.scale ? scale_partials : nullptr, zero_ints, n_zero);
+}
+
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
                          float *g_grid, float *scale_partials, int *zero_ints, int n_zero,
                          cudaStream_t s) {
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
+  if (a.tck) {
+    if (g_probs || g_voxels || a.Vz != a.V || !a.logsum) {
+      set_error("drc_blurz_bwd: fast ray state needs a cubic grid, log-sum DRC and no g_probs / g_voxels");
+      return DPC_ERR_ARG;
+    }
+    DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_fast<V, R>(a, c, z_taps<R>(tz, kz, r), g_mask,
+                                                                g_depth, g_grid, scale_partials,
+                                                                zero_ints, n_zero, s)));
+    return check_launch("drc_blurz_bwd_fast");
+  }
   if (g_probs || g_voxels) {
     DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_one<V, R, true>(
                                               a, c, z_taps<R>(tz, kz, r), g_mask, g_depth, g_probs,

@@ -56,8 +56,9 @@ def _f32(t, name, shape=None):
     return t.contiguous()
 
 
-def make_params(cfg, P, N, flip_y=True):
-    """dpc_params from the reference's cfg keys (default_config.yaml:72-83)."""
+def make_params(cfg, P, N, flip_y=True, outputs=0):
+    """dpc_params from the reference's cfg keys (default_config.yaml:72-83); ``outputs`` =
+    the optional outputs (OUT_VOXELS | OUT_PROBS) the whole-path forward materialises."""
     V = int(cfg.vox_size)
     vz = int(getattr(cfg, "vox_size_z", -1))
     Vz = V if vz == -1 else vz
@@ -67,7 +68,7 @@ def make_params(cfg, P, N, flip_y=True):
                        max_depth=float(getattr(cfg, "max_depth", 10.0)),
                        drc_clip=float(getattr(cfg, "drc_logsum_clip_val", 1e-5)),
                        drc_logsum=1 if getattr(cfg, "drc_logsum", True) else 0,
-                       flip_y=1 if flip_y else 0)
+                       flip_y=1 if flip_y else 0, outputs=int(outputs))
 
 
 def host_taps(kernel):
@@ -140,6 +141,7 @@ class ProjectFn(torch.autograd.Function):
         lib = _lib.load()
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
+        params.outputs = (_lib.OUT_VOXELS if want_voxels else 0) | (_lib.OUT_PROBS if want_probs else 0)
         f32 = dict(dtype=torch.float32, device=dev)
         tr_pc = torch.empty(P, N, 3, **f32)
         mask = torch.empty(P, V, V, **f32)
