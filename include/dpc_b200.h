@@ -42,7 +42,7 @@ extern "C" {
 #define DPC_API
 #endif
 
-#define DPC_B200_VERSION 130
+#define DPC_B200_VERSION 140
 #define DPC_MAX_TAPS 21
 
 typedef enum {
@@ -250,6 +250,43 @@ DPC_API int dpc_select_points(int P, int replicas, int N_src, int M, int C, cons
 DPC_API int dpc_replica_reduce(int P, int replicas, int N_src, int M, int C, const float *g_rep,
                        const int32_t *sel /*NULL ok*/, int32_t *inv_scratch /*NULL ok*/,
                        float *g_cloud, void *stream);
+
+/* ---- a14 / f3 (next row): the point-feature (RGB) branch --------------------
+ * Specification: the TF original util/point_cloud.py:99-129 (feature scatter),
+ * :148-154 convolve_rgb, :244-262 (clip, division by the blurred occupancy, Y
+ * flip) and project_volume_rgb_integral (util/drc.py:132-142 in the torch
+ * port).  The torch port of this branch does not run (point_cloud_to.py:64,
+ * drc.py:137), so parity is pinned to oracle/rgb.py's restatement of the TF file
+ * only.  Feature grids are channel-planar: fgrid [P,C,Vz,V,V], C <= 4.
+ *
+ * fgrid[b,c,cell+corner] += w(corner) * feat[b,n,c] over the valid points of
+ * tr_pc [P,N,3] (the same trilinear weights as dpc_scatter_fwd); feat [P,N,C]. */
+DPC_API int dpc_feat_scatter_fwd(const dpc_params *p, int C, const float *tr_pc, const float *feat,
+                         float *fgrid, void *stream);
+/* Adjoint: g_feat [P,N,C] and g_tr_pc [P,N,3] (NULL ok: pc_rgb_stop_points_gradient).
+ * raw (NULL ok): the forward's fgrid; when given, g_fgrid counts only where
+ * 0 <= raw <= 1 -- the gate of the clip that precedes the blur (point_cloud.py:247). */
+DPC_API int dpc_feat_scatter_bwd(const dpc_params *p, int C, const float *tr_pc, const float *feat,
+                         const float *g_fgrid, const float *raw /*NULL ok*/, float *g_feat,
+                         float *g_tr_pc /*NULL ok*/, void *stream);
+/* dpc_blur3d with clamp(src, 0, 1) taken on the way in (point_cloud.py:246-248).
+ * For feature grids pass params with P = P * C. */
+DPC_API int dpc_blur3d_clamped(const dpc_params *p, const float *src, float *dst,
+                       const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                       const float *taps_z_host, int kz, void *stream);
+/* Colour integral: proj_rgb [P,V,V,C] = sum_{k<Vz} probs[k] f_c[k] + probs[Vz]
+ * (white background), f = fgrid, / (div + eps) when div [P,Vz,V,V] is given
+ * (pc_rgb_divide_by_occupancies), clipped to [0,1] when clip_after
+ * (pc_rgb_clip_after_conv).  probs [Vz+1,P,V,V] is in output row order (as
+ * dpc_project_fwd writes it); the grids are read with the Y flip of p->flip_y.
+ * voxels_rgb (NULL ok): [P,Vz,V,V,C], the reference's "voxels_rgb" output. */
+DPC_API int dpc_colour_fwd(const dpc_params *p, int C, const float *probs, const float *fgrid,
+                   const float *div /*NULL ok*/, float eps, int clip_after, float *proj_rgb,
+                   float *voxels_rgb /*NULL ok*/, void *stream);
+/* Adjoint: g_probs [Vz+1,P,V,V] and g_fgrid [P,C,Vz,V,V] (both fully written). */
+DPC_API int dpc_colour_bwd(const dpc_params *p, int C, const float *probs, const float *fgrid,
+                   const float *div /*NULL ok*/, float eps, int clip_after,
+                   const float *g_proj_rgb, float *g_probs, float *g_fgrid, void *stream);
 
 /* ---- f4 (next row): util/point_cloud_distance.py:25-40 point_cloud_distance
  * (the kernel of run/eval_chamfer_to.py:24-44 compute_distance) -------------

@@ -9,9 +9,10 @@ from . import _lib
 from .gauss_kernel import gauss_kernel_1d, separable_kernels, smoothing_kernel
 from .point_cloud import (pc_perspective_transform, pointcloud2voxels3d_fast,
                           pointcloud_project_fast, smoothen_voxels3d, set_outputs,
-                          set_deterministic, options, pc_point_dropout,
+                          set_deterministic, options, pc_point_dropout, convolve_rgb,
                           pointcloud_project_replicated)
-from .drc import drc_depth_projection, drc_event_probabilities, drc_projection
+from .drc import (drc_depth_projection, drc_event_probabilities, drc_projection,
+                  project_volume_rgb_integral)
 from .pipeline import GraphedSteps, HostPipeline
 from .losses import add_proj_loss, proj_loss_pose_candidates
 from .point_cloud_distance import chamfer_distances, point_cloud_distance
@@ -21,7 +22,8 @@ __all__ = [
     "smoothen_voxels3d", "drc_projection", "drc_depth_projection", "drc_event_probabilities",
     "smoothing_kernel", "gauss_kernel_1d", "separable_kernels",
     "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "add_proj_loss", "proj_loss_pose_candidates", "point_cloud_distance", "chamfer_distances",
-    "pc_point_dropout", "pointcloud_project_replicated",
+    "pc_point_dropout", "pointcloud_project_replicated", "convolve_rgb",
+    "project_volume_rgb_integral",
     "library_path", "version",
 ]
 

@@ -68,6 +68,14 @@ SIGNATURES = {
     "dpc_point_dropout_indices": [c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p],
     "dpc_select_points": [c_int] * 5 + [c_void_p] * 3 + [c_void_p],
     "dpc_replica_reduce": [c_int] * 5 + [c_void_p] * 4 + [c_void_p],
+    "dpc_feat_scatter_fwd": [_P, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dpc_feat_scatter_bwd": [_P, c_int] + [c_void_p] * 6 + [c_void_p],
+    "dpc_blur3d_clamped": [_P, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                           c_void_p],
+    "dpc_colour_fwd": [_P, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_int, c_void_p,
+                       c_void_p, c_void_p],
+    "dpc_colour_bwd": [_P, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_int, c_void_p,
+                       c_void_p, c_void_p, c_void_p],
     "dpc_candidate_loss_fwd": [c_int] * 4 + [c_void_p] * 6 + [c_void_p],
     "dpc_candidate_loss_bwd": [c_int] * 4 + [c_void_p] * 5 + [ctypes.c_float, c_void_p, c_void_p],
     "dpc_point_cloud_distance": [c_int, c_int] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p],

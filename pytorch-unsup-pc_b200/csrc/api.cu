@@ -242,6 +242,64 @@ int dpc_blur3d(const dpc_params *p, const float *src, float *dst, const float *t
   return launch_blur_z(dst, dst, p->P, p->Vz, p->V, tz, kz, s);
 }
 
+int dpc_blur3d_clamped(const dpc_params *p, const float *src, float *dst, const float *tx, int kx,
+                       const float *ty, int ky, const float *tz, int kz, void *stream) {
+  DPC_TRY(check_params(p, false));
+  DPC_REQUIRE(src); DPC_REQUIRE(dst);
+  DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
+  DPC_TRY(check_taps(tz, kz, "taps_z"));
+  cudaStream_t s = (cudaStream_t)stream;
+  BlurXYArgs a;
+  a.src = src; a.dst = dst; a.bits_out = nullptr; a.bits_in = nullptr;
+  a.planes = p->P * p->Vz; a.V = p->V; a.clamp_in = true;
+  DPC_TRY(launch_blur_xy(a, tx, kx, ty, ky, s));
+  return launch_blur_z(dst, dst, p->P, p->Vz, p->V, tz, kz, s);
+}
+
+// ---- a14 / f3: point-feature (RGB) branch --------------------------------------
+static int check_channels(int C) {
+  if (C < 1 || C > feat_max_channels()) {
+    set_error("feature channels=%d unsupported (1..%d)", C, feat_max_channels());
+    return DPC_ERR_ARG;
+  }
+  return DPC_OK;
+}
+
+int dpc_feat_scatter_fwd(const dpc_params *p, int C, const float *tr_pc, const float *feat,
+                         float *fgrid, void *stream) {
+  DPC_TRY(check_params(p, true)); DPC_TRY(check_channels(C));
+  DPC_REQUIRE(tr_pc); DPC_REQUIRE(feat); DPC_REQUIRE(fgrid);
+  return launch_feat_scatter(tr_pc, feat, p->P, p->N, C, p->Vz, p->V, fgrid, (cudaStream_t)stream);
+}
+
+int dpc_feat_scatter_bwd(const dpc_params *p, int C, const float *tr_pc, const float *feat,
+                         const float *g_fgrid, const float *raw, float *g_feat, float *g_tr_pc,
+                         void *stream) {
+  DPC_TRY(check_params(p, true)); DPC_TRY(check_channels(C));
+  DPC_REQUIRE(tr_pc); DPC_REQUIRE(feat); DPC_REQUIRE(g_fgrid); DPC_REQUIRE(g_feat);
+  return launch_feat_gather_bwd(tr_pc, feat, g_fgrid, raw, p->P, p->N, C, p->Vz, p->V, g_feat,
+                                g_tr_pc, (cudaStream_t)stream);
+}
+
+int dpc_colour_fwd(const dpc_params *p, int C, const float *probs, const float *fgrid,
+                   const float *div, float eps, int clip_after, float *proj_rgb, float *voxels_rgb,
+                   void *stream) {
+  DPC_TRY(check_params(p, false)); DPC_TRY(check_channels(C));
+  DPC_REQUIRE(probs); DPC_REQUIRE(fgrid); DPC_REQUIRE(proj_rgb);
+  return launch_colour_fwd(probs, fgrid, div, eps, clip_after, p->P, C, p->Vz, p->V, p->flip_y,
+                           proj_rgb, voxels_rgb, (cudaStream_t)stream);
+}
+
+int dpc_colour_bwd(const dpc_params *p, int C, const float *probs, const float *fgrid,
+                   const float *div, float eps, int clip_after, const float *g_proj_rgb,
+                   float *g_probs, float *g_fgrid, void *stream) {
+  DPC_TRY(check_params(p, false)); DPC_TRY(check_channels(C));
+  DPC_REQUIRE(probs); DPC_REQUIRE(fgrid); DPC_REQUIRE(g_proj_rgb); DPC_REQUIRE(g_probs);
+  DPC_REQUIRE(g_fgrid);
+  return launch_colour_bwd(probs, fgrid, div, eps, clip_after, p->P, C, p->Vz, p->V, p->flip_y,
+                           g_proj_rgb, g_probs, g_fgrid, (cudaStream_t)stream);
+}
+
 int dpc_drc_fwd(const dpc_params *p, const float *voxels, float *mask, float *depth, float *probs,
                 void *stream) {
   DPC_TRY(check_params(p, false));

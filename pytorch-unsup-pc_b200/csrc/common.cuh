@@ -209,6 +209,20 @@ int launch_select_points(const float *points, const int *sel, int P, int R, int 
 int launch_replica_reduce(const float *g_rep, const int *sel, int *inv, int P, int R, int N_src,
                           int M, int C, float *g_cloud, cudaStream_t s);
 
+// ---- point-feature (RGB) branch (feature.cu) -----------------------------------
+int feat_max_channels();
+int launch_feat_scatter(const float *tr_pc, const float *feat, int P, int N, int C, int Vz, int V,
+                        float *grid, cudaStream_t s);
+int launch_feat_gather_bwd(const float *tr_pc, const float *feat, const float *g_grid,
+                           const float *raw, int P, int N, int C, int Vz, int V, float *g_feat,
+                           float *g_trpc, cudaStream_t s);
+int launch_colour_fwd(const float *probs, const float *fgrid, const float *div, float eps,
+                      int clip_after, int P, int C, int Vz, int V, int flip_y, float *proj_rgb,
+                      float *voxels_rgb, cudaStream_t s);
+int launch_colour_bwd(const float *probs, const float *fgrid, const float *div, float eps,
+                      int clip_after, int P, int C, int Vz, int V, int flip_y, const float *g_proj,
+                      float *g_probs, float *g_fgrid, cudaStream_t s);
+
 // ---- candidate-selection projection loss (candidate_loss.cu) -----------------
 int candidate_loss_max_candidates();
 int launch_candidate_loss_fwd(const float *gt, const float *pred, const float *weights, int BV,

@@ -444,3 +444,103 @@ class SelectPointsFn(torch.autograd.Function):
                                         _ptr(g), _stream(dev))
         _lib.check(st, "replica_reduce")
         return g, None, None
+
+
+class FeatGridFn(torch.autograd.Function):
+    """Feature scatter (+ clip + per-channel blur): tr_pc [P,N,3], feat [P,N,C] -> planar
+    feature grid [P,C,Vz,V,V]  (TF original point_cloud.py:99-129, 244-249, 148-154).
+    ``clip``: clamp(raw, 0, 1) before the blur; its gate is applied inside the gather of the
+    backward.  ``taps`` None: no clip, no blur."""
+
+    @staticmethod
+    def forward(ctx, tr_pc, feat, params, taps, clip):
+        lib = _lib.load()
+        dev = tr_pc.device
+        P, N, Vz, V = params.P, params.N, params.Vz, params.V
+        C = feat.shape[-1]
+        raw = torch.empty(P, C, Vz, V, V, dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            st = lib.dpc_feat_scatter_fwd(ctypes.byref(params), C, _ptr(tr_pc), _ptr(feat), _ptr(raw),
+                                          _stream(dev))
+        _lib.check(st, "feat_scatter_fwd")
+        out = raw
+        pc = None
+        if taps is not None:
+            pc = _lib.Params.from_buffer_copy(params)
+            pc.P = P * C
+            out = torch.empty_like(raw)
+            fn = lib.dpc_blur3d_clamped if clip else lib.dpc_blur3d
+            with _on_device(dev):
+                st = fn(ctypes.byref(pc), _ptr(raw), _ptr(out), *_tap_args(taps), _stream(dev))
+            _lib.check(st, "blur3d(features)")
+        gated = bool(clip and taps is not None)
+        ctx.save_for_backward(tr_pc, feat, raw if gated else None)
+        ctx.params, ctx.pc, ctx.taps = params, pc, taps
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        tr_pc, feat, raw = ctx.saved_tensors
+        params = ctx.params
+        dev = tr_pc.device
+        C = feat.shape[-1]
+        g = _f32(g_out, "g_fgrid", (params.P, C, params.Vz, params.V, params.V))
+        if ctx.taps is not None:
+            rev = tuple(torch.flip(k, [0]).contiguous() for k in ctx.taps)
+            gb = torch.empty_like(g)
+            with _on_device(dev):
+                st = lib.dpc_blur3d(ctypes.byref(ctx.pc), _ptr(g), _ptr(gb), *_tap_args(rev),
+                                    _stream(dev))
+            _lib.check(st, "blur3d(feature adjoint)")
+            g = gb
+        g_feat = torch.empty_like(feat)
+        g_trpc = torch.empty_like(tr_pc) if ctx.needs_input_grad[0] else None
+        with _on_device(dev):
+            st = lib.dpc_feat_scatter_bwd(ctypes.byref(params), C, _ptr(tr_pc), _ptr(feat), _ptr(g),
+                                          _ptr(raw), _ptr(g_feat), _ptr(g_trpc), _stream(dev))
+        _lib.check(st, "feat_scatter_bwd")
+        return g_trpc, g_feat, None, None, None
+
+
+class ColourFn(torch.autograd.Function):
+    """Colour integral along the rays (drc.py:132-142 project_volume_rgb_integral) with the
+    optional division by the blurred occupancy and clip-after-blur of point_cloud.py:256-262
+    applied on the fly: probs [Vz+1,P,V,V], fgrid [P,C,Vz,V,V] (+ div [P,Vz,V,V]) ->
+    proj_rgb [P,V,V,C] and, on request, voxels_rgb [P,Vz,V,V,C] (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, probs, fgrid, div, eps, clip_after, params, want_voxels):
+        lib = _lib.load()
+        dev = probs.device
+        P, Vz, V = params.P, params.Vz, params.V
+        C = fgrid.shape[1]
+        proj = torch.empty(P, V, V, C, dtype=torch.float32, device=dev)
+        vox = torch.empty(P, Vz, V, V, C, dtype=torch.float32, device=dev) if want_voxels else None
+        with _on_device(dev):
+            st = lib.dpc_colour_fwd(ctypes.byref(params), C, _ptr(probs), _ptr(fgrid), _ptr(div),
+                                    ctypes.c_float(eps), int(bool(clip_after)), _ptr(proj), _ptr(vox),
+                                    _stream(dev))
+        _lib.check(st, "colour_fwd")
+        ctx.save_for_backward(probs, fgrid, div)
+        ctx.params, ctx.eps, ctx.clip_after = params, float(eps), bool(clip_after)
+        if vox is not None:
+            ctx.mark_non_differentiable(vox)
+        return proj, vox
+
+    @staticmethod
+    def backward(ctx, g_proj, _g_vox):
+        lib = _lib.load()
+        probs, fgrid, div = ctx.saved_tensors
+        params = ctx.params
+        dev = probs.device
+        C = fgrid.shape[1]
+        g_proj = _f32(g_proj, "g_proj_rgb", (params.P, params.V, params.V, C))
+        g_probs = torch.empty_like(probs)
+        g_fgrid = torch.empty_like(fgrid)
+        with _on_device(dev):
+            st = lib.dpc_colour_bwd(ctypes.byref(params), C, _ptr(probs), _ptr(fgrid), _ptr(div),
+                                    ctypes.c_float(ctx.eps), int(ctx.clip_after), _ptr(g_proj),
+                                    _ptr(g_probs), _ptr(g_fgrid), _stream(dev))
+        _lib.check(st, "colour_bwd")
+        return g_probs, g_fgrid, None, None, None, None, None

@@ -87,14 +87,43 @@ def pc_perspective_transform(cfg, point_cloud, transform, predicted_translation=
 def pointcloud2voxels3d_fast(cfg, pc, rgb):
     """pc [P,N,3] (already transformed) -> (voxels [P,Vz,V,V], None)
     (point_cloud_to.py:10-87).  Points outside [-0.5,0.5]^3 are dropped."""
-    if rgb is not None:
-        raise NotImplementedError("the rgb branch is broken in the reference "
-                                  "(point_cloud_to.py:64) and not part of this path")
     pts = ops._f32(pc, "pc")
     if pts.dim() != 3 or pts.shape[-1] != 3:
         raise ValueError("pc must be [P,N,3], got %s" % (tuple(pts.shape),))
     params = ops.make_params(cfg, pts.shape[0], pts.shape[1])
-    return ops.ScatterFn.apply(pts, params, _scatter_mode()), None
+    voxels = ops.ScatterFn.apply(pts, params, _scatter_mode())
+    if rgb is None:
+        return voxels, None
+    # the rgb part of the TF original (point_cloud.py:111-121; the torch port's :61-69 is broken):
+    # voxels_rgb [P,Vz,V,V,C], the same trilinear weights times the point's features
+    col = _features(rgb, pts)
+    tr = pts.detach() if getattr(cfg, "pc_rgb_stop_points_gradient", False) else pts
+    planar = ops.FeatGridFn.apply(tr, col, params, None, False)
+    return voxels, planar.permute(0, 2, 3, 4, 1)
+
+
+def _features(rgb, pts):
+    col = ops._f32(rgb, "rgb")
+    if col.dim() != 3 or col.shape[:2] != pts.shape[:2] or not 1 <= col.shape[2] <= 4:
+        raise ValueError("rgb must be [P,N,C] with 1 <= C <= 4 for points %s, got %s"
+                         % (tuple(pts.shape), tuple(col.shape)))
+    return col
+
+
+def convolve_rgb(cfg, voxels_rgb, kernel):
+    """voxels_rgb [P,Vz,V,V,C] -> same: the three 1-D blurs on every channel separately
+    (point_cloud_to.py:106-114; TF point_cloud.py:148-154)."""
+    vox = ops._f32(voxels_rgb, "voxels_rgb")
+    if vox.dim() != 5:
+        raise ValueError("voxels_rgb must be [P,Vz,V,V,C], got %s" % (tuple(vox.shape),))
+    P, Vz, V, V2, C = vox.shape
+    params = ops.make_params(cfg, P * C, 0)
+    if (params.Vz, params.V, params.V) != (Vz, V, V2):
+        raise ValueError("voxels_rgb shape %s does not match cfg grid %s"
+                         % (tuple(vox.shape), (params.Vz, params.V, params.V)))
+    planar = vox.permute(0, 4, 1, 2, 3).reshape(P * C, Vz, V, V).contiguous()
+    out = ops.BlurFn.apply(planar, params, ops.host_taps(kernel))
+    return out.reshape(P, C, Vz, V, V).permute(0, 2, 3, 4, 1)
 
 
 def smoothen_voxels3d(cfg, voxels, kernel):
@@ -177,8 +206,9 @@ def pointcloud_project_replicated(cfg, point_cloud, transform, predicted_transla
     ``indices`` ([P,M], distinct per row) supplies the selection instead."""
     _check_quaternion_cfg(cfg)
     if all_rgb is not None:
-        raise NotImplementedError("all_rgb: the rgb branch is broken in the reference "
-                                  "(point_cloud_to.py:64) and not part of this path")
+        raise NotImplementedError("all_rgb: project the features with pointcloud_project_fast on "
+                                  "pc_point_dropout's outputs; the replica-aware entry point "
+                                  "carries no point features")
     if getattr(cfg, "ptn_max_projection", False):
         raise NotImplementedError("ptn_max_projection is broken in the reference "
                                   "(point_cloud_to.py:234,242) and not supported")
@@ -229,9 +259,6 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation, 
     The blur always runs when ``kernel`` is given (the reference's CUDA branch,
     :207-209); ``kernel=None`` means no blur with the TF original's layout."""
     _check_quaternion_cfg(cfg)
-    if all_rgb is not None:
-        raise NotImplementedError("all_rgb: the rgb branch is broken in the reference "
-                                  "(point_cloud_to.py:64) and not part of this path")
     if getattr(cfg, "ptn_max_projection", False):
         raise NotImplementedError("ptn_max_projection is broken in the reference "
                                   "(point_cloud_to.py:234,242) and not supported")
@@ -243,16 +270,47 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation, 
     trans = ops._f32(predicted_translation, "predicted_translation", (P, 3))
     scale = _vec(scaling_factor, "scaling_factor", P)
     focal = _vec(focal_length, "focal_length", P)
+    col = None if all_rgb is None else _features(all_rgb, pts)
     params = ops.make_params(cfg, P, N, flip_y=True)
+    taps = ops.host_taps(kernel)
+    # the colour integral needs the ray-event probabilities, asked for or not
     mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
-        pts, quat, trans, focal, scale, params, ops.host_taps(kernel),
-        _options["voxels"], _options["drc_probs"], _scatter_mode(), _options["plane_local"])
+        pts, quat, trans, focal, scale, params, taps,
+        _options["voxels"], _options["drc_probs"] or col is not None, _scatter_mode(),
+        _options["plane_local"])
+    voxels_rgb = proj_rgb = None
+    if col is not None:
+        voxels_rgb, proj_rgb = _project_features(cfg, tr_pc, col, probs, taps, P, N)
     return {
         "proj": mask.unsqueeze(-1),
         "voxels": None if voxels is None else voxels.unsqueeze(-1),
         "tr_pc": tr_pc,
-        "voxels_rgb": None,
-        "proj_rgb": None,
-        "drc_probs": None if probs is None else probs.unsqueeze(-1),
+        "voxels_rgb": voxels_rgb,
+        "proj_rgb": proj_rgb,
+        "drc_probs": None if (probs is None or not _options["drc_probs"]) else probs.unsqueeze(-1),
         "proj_depth": depth.unsqueeze(-1),
     }
+
+
+def _project_features(cfg, tr_pc, col, probs, taps, P, N):
+    """The rgb branch of the TF original's pointcloud_project_fast (point_cloud.py:244-277; the
+    torch port's branch is broken, point_cloud_to.py:64): feature scatter with the occupancy's
+    weights, clip + per-channel blur, optional division by the blurred raw occupancy, optional
+    clip after the blur, Y flip and colour integral with a white background.
+    Returns (voxels_rgb [P,Vz,V,V,C] -- not differentiable --, proj_rgb [P,V,V,C])."""
+    clip_after = bool(getattr(cfg, "pc_rgb_clip_after_conv", False))
+    params = ops.make_params(cfg, P, N, flip_y=True)
+    tr = tr_pc.detach() if getattr(cfg, "pc_rgb_stop_points_gradient", False) else tr_pc
+    fgrid = ops.FeatGridFn.apply(tr, col, params, taps, not clip_after)
+    div, eps = None, 0.0
+    if getattr(cfg, "pc_rgb_divide_by_occupancies", False):
+        if taps is None:
+            raise ValueError("pc_rgb_divide_by_occupancies needs a smoothing kernel "
+                             "(point_cloud.py:258 blurs the raw occupancy)")
+        with torch.no_grad():       # stop_gradient(voxels_raw), point_cloud.py:257
+            raw = ops.ScatterFn.apply(tr_pc.detach(), params, _scatter_mode())
+            div = ops._blur3d(raw, params, taps)
+        eps = float(getattr(cfg, "pc_rgb_divide_by_occupancies_epsilon", 0.01))
+    proj_rgb, voxels_rgb = ops.ColourFn.apply(probs, fgrid, div, eps, clip_after, params,
+                                              _options["voxels"])
+    return voxels_rgb, proj_rgb

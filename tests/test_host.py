@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     # the ctypes prototypes cover exactly the declared surface
     assert declared == set(dpc._lib.SIGNATURES)
-    assert dpc.version() == 130
+    assert dpc.version() == 140
 
 
 def test_workspace_bytes_and_params_struct():
