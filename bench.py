@@ -68,13 +68,14 @@ def stage_algorithmic_bytes(N, V, Vz):
             "blur_xy_bwd": 5 * G, "gather_pose_bwd": G + 36 * N}
 
 
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's kernel at
-# workload A, from the committed `ncu --set full` capture profiles/r01_ncu_full_step_plane_local_v2.csv
-# (cold L2: ncu flushes the caches before every replay).  None = not captured for that workload.
+# DRAM bytes per whole-batch launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's
+# kernel(s) at workload A, from the committed `ncu --set full` capture NCU_CAPTURE (cold L2: ncu
+# flushes the caches before every replay).  None = not captured for that workload.
+NCU_CAPTURE = "profiles/r01_ncu_full_step_fast_ray_state.csv"
 NCU_TRAFFIC_BYTES = {
-    "A": {"pose_scatter": 6.16e6 + 8.72e6, "blur_xy_fwd": 7.46e6 + 12.07e6,
-          "blurz_drc_fwd": 67.13e6 + 11.02e6, "drc_blurz_bwd": 69.25e6 + 21.03e6,
-          "blur_xy_bwd": 77.09e6 + 3.66e6, "gather_pose_bwd": 23.12e6 + 0.0},
+    "A": {"pose_scatter": 6.16e6 + 8.72e6, "blur_xy_fwd": 7.46e6 + 12.18e6,
+          "blurz_drc_fwd": 67.16e6 + 14.18e6, "drc_blurz_bwd": 71.37e6 + 24.96e6,
+          "blur_xy_bwd": 77.22e6 + 4.59e6, "gather_pose_bwd": 23.12e6 + 0.0},
 }
 
 
@@ -445,6 +446,7 @@ def run_b200(args, rank, world, local_rank):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     stages = dict(zip(_lib.PROFILE_STAGES, [float(x) for x in stage_ms]))
+    n_chunks = lib.dpc_project_chunks(ctypes.byref(params))
     sbytes = stage_algorithmic_bytes(N, V, Vz)
     top = max((k for k in stages if k != "memset"), key=lambda k: stages[k])
     achieved = sbytes[top] * P / (stages[top] * 1e-3) / 1e9
@@ -481,13 +483,18 @@ def run_b200(args, rank, world, local_rank):
                        "step's H2D / kernels / D2H overlap the neighbouring steps')",
                 "mode": e2e_mode},
         "e2e_replica_aware": e2e_rep,
-        "gpu_launches": (6 if args.global_grid else 7) * args.steps,
+        # kernels per chunk: pose_cells + bin_points (or pose_scatter), blur_xy, blurz_drc_fwd |
+        # drc_blurz_bwd, blur_xy, gather_pose_bwd -- times the chunks the batch is split into
+        "gpu_launches": (6 if args.global_grid else 7) * n_chunks * args.steps,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (None if args.global_grid else
                                  NCU_TRAFFIC_BYTES.get(args.workload, {}).get(top)),
-                     "traffic_source": "profiles/r01_ncu_full_step_plane_local_v2.csv (ncu --set full, "
-                                       "dram read + write per launch, cold L2)",
+                     "traffic_source": NCU_CAPTURE + " (ncu --set full, dram read + write of one "
+                                       "whole-batch launch, cold L2)",
+                     "note": "kernel_ms and the byte counts are per whole-batch launch "
+                             "(dpc_project_profile runs one chunk); the timed step runs %d "
+                             "half-batch launches of every kernel on two streams" % n_chunks,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": sbytes[top] * P,
                      "kernel_ms": stages[top]},

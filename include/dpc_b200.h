@@ -154,6 +154,12 @@ DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const floa
                     float *voxels /*NULL ok*/, float *probs /*NULL ok*/,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* How many chunks of projections dpc_project_fwd / dpc_project_bwd split this batch into (each
+ * chunk is one set of kernel launches on one of two internal streams that fork from and join
+ * `stream`): 2 half-batches for P >= 64, else 1; DPC_CHUNK=<projections> (environment)
+ * overrides.  bench.py counts its launches with it. */
+DPC_API int dpc_project_chunks(const dpc_params *p);
+
 /* Backward of the whole path.  g_grid is a [P,Vz,V,V] scratch buffer.
  * Upstream grads: g_mask, g_depth [P,V,V]; g_probs, g_voxels, g_tr_pc optional.
  * Outputs: g_points [P,N,3], g_quat [P,4]; g_trans [P,3], g_focal [P],

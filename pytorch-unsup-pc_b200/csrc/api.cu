@@ -380,6 +380,12 @@ static int chunk_size(const dpc_params *p) {
   return p->P;
 }
 
+int dpc_project_chunks(const dpc_params *p) {
+  if (!p || p->P < 1) return 0;
+  const int c = chunk_size(p);
+  return c < p->P ? (p->P + c - 1) / c : 1;
+}
+
 struct FwdPtrs {
   const float *points, *quat, *trans, *focal, *scale;
   float *tr_pc, *grid_b; uint32_t *bits; float *mask, *depth, *voxels, *probs;

@@ -52,9 +52,7 @@ def test_cpu_tensors_are_refused():
 def test_unsupported_reference_branches_raise():
     import pytorch_unsup_pc_b200 as dpc
     cfg = default_cfg(vox_size=32)
-    with pytest.raises(NotImplementedError):
-        dpc.pointcloud_project_fast(cfg, torch.zeros(1, 4, 3), torch.ones(1, 4), None,
-                                    torch.zeros(1, 4, 3))
+    # (all_rgb is supported: tests/test_rgb.py)
     with pytest.raises(NotImplementedError):
         dpc.pointcloud_project_fast(default_cfg(pose_quaternion=False), torch.zeros(1, 4, 3),
                                     torch.ones(1, 4, 4), None, None)
