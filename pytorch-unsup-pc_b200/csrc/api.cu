@@ -633,9 +633,6 @@ static int project_bwd_impl(const dpc_params *p, const Replica &rep, const float
   DPC_TRY(check_ws(p, workspace, workspace_bytes));
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
-  // The plane gather pays off while several CTAs share an SM (V <= 64); a 128^2
-  // plane takes the whole SM's shared memory and its gather runs with nothing to
-  // overlap it (measured at workload B: 1269 vs 773 us), so 128^3 gathers from the grid.
   void *fast_rays = nullptr;
   if (plane_local_ok(p) && fast_ray_state(p, cells, DPC_SCATTER_ATOMIC)) {
     if (g_probs || g_voxels) {
@@ -645,7 +642,12 @@ static int project_bwd_impl(const dpc_params *p, const Replica &rep, const float
     }
     fast_rays = const_cast<void *>(cells);
   }
-  if (!plane_local_ok(p) || p->V > 64) cells = nullptr;
+  // The plane gather (backward of the plane-local scatter) runs at every grid size: with the
+  // one-tile blur at 128^2 two CTAs share an SM and cover each other's gather (workload B:
+  // blur XY adjoint 569 -> 601 us, pose adjoint 140 -> 44 us).  DPC_GATHER128=0 restores the
+  // gather from the gradient grid at V = 128 for A/B runs.
+  static const bool grid_gather128 = getenv("DPC_GATHER128") && atoi(getenv("DPC_GATHER128")) == 0;
+  if (!plane_local_ok(p) || (p->V > 64 && grid_gather128)) cells = nullptr;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
                   g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
                   const_cast<void *>(cells), rep, fast_rays};

@@ -62,19 +62,24 @@ struct XYCfg {
   static constexpr int J = 16;                       // outputs per line per thread
   static constexpr int W = J + 2 * R;                // window positions (even)
   static constexpr int W2 = W / 2;                   // LDS.128 per window
-  static constexpr int RH = V < 64 ? V : 64;         // plane rows staged per X-pass round
+#ifndef DPC_XY_RH128
+#define DPC_XY_RH128 128
+#endif
+  // plane rows staged per X-pass round: the whole plane (one tile, reused for the transposed
+  // layout).  DPC_XY_RH128=64: two rounds of 64 rows at V = 128 (two tiles, 115 KB, 1 CTA/SM)
+  static constexpr int RH = V <= 64 ? V : DPC_XY_RH128;
   static constexpr int S0 = V + 2 * R;               // positions a line must hold
   static constexpr int S = (S0 % 4 == 2) ? S0 : S0 + 2;   // stride in pairs, S/2 odd
   static constexpr int XTASKS = (RH / 2) * (V / J);
   static constexpr int YTASKS = (V / 2) * (V / J);
-  static constexpr int THREADS = YTASKS < 128 ? YTASKS : (V == 128 ? 256 : 128);
+  static constexpr int THREADS = YTASKS < 128 ? YTASKS : (V == 128 ? (RH == V ? 512 : 256) : 128);
   static constexpr int FILL_ITEMS = (RH / 2) * (V / 4);
   // V <= 64: the X-pass results wait in registers while the tile is reused for
   // the transposed layout, so one tile suffices (22 KB -> 9-10 CTAs per SM)
   static constexpr bool ONE_TILE = (RH == V);
   static constexpr int TILE_LINES = ONE_TILE ? V / 2 : RH / 2 + V / 2;
   static constexpr size_t SMEM = (size_t)TILE_LINES * S * sizeof(float2);
-  static constexpr int MINB = V == 64 ? 9 : 1;
+  static constexpr int MINB = V == 64 ? 9 : (V == 128 && RH == V ? 2 : 1);
   static_assert(V % 32 == 0, "V must be a multiple of 32");
   static_assert(FILL_ITEMS % THREADS == 0, "fill loop must be warp-uniform");
   static_assert(!ONE_TILE || XTASKS == THREADS, "one-tile mode: one X task per thread");
@@ -326,11 +331,10 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
     /* the gather tile lives behind the window tiles when it cannot overlay them */            \
     const size_t smem = C::SMEM + ((PT && MO && C::YTASKS != C::THREADS) ? V * V * 4 : 0) +    \
                         ((PT && WB) ? C::RH * V / 8 : 0);                                      \
-    static bool attr_done = false;                                                             \
-    if (!attr_done) {                                                                          \
+    static DeviceOnce attr_once;                                                               \
+    if (attr_once.first()) {                                                                   \
       cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT>,                               \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-      attr_done = true;                                                                        \
     }                                                                                          \
     blur_xy_kernel<V, R, CL, WB, MO, PT><<<g, t, smem, s>>>(a.src, a.dst, a.bits_out,          \
                                                             a.bits_in, KX, KY, a.cells, a.part, \

@@ -46,6 +46,20 @@ inline int effective_radius(const float *host, int n) {
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
 
+// One-time-per-DEVICE flag for cudaFuncSetAttribute (function attributes are per device; a
+// process that drives several GPUs must opt every one of them in): `static DeviceOnce once;
+// if (once.first()) cudaFuncSetAttribute(...)`.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const bool f = !done[dev];
+    done[dev] = true;
+    return f;
+  }
+};
+
 // ---- kernel launchers (defined in the .cu files) ---------------------------
 struct PoseArgs {
   const float *points, *quat, *trans, *focal;

@@ -761,11 +761,10 @@ static void launch_bwd_vz(const DrcArgs &a, const RayConst &c, const Taps<R> &ta
   constexpr int L = RingLen<R>::L;
   const int nblk = (a.Vz + L - 1) / L;
   const size_t smem = (size_t)(a.Vz + nblk) * kBwdThreads * sizeof(float2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(drc_blurz_bwd_kernel<V, R, EXTRA, VZ>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
   }
   const int blocks = a.P * (V * V / 2) / kBwdThreads;
   drc_blurz_bwd_kernel<V, R, EXTRA, VZ><<<blocks, kBwdThreads, smem, s>>>(
@@ -794,11 +793,10 @@ static void launch_bwd_fast(const DrcArgs &a, const RayConst &c, const Taps<R> &
                             float *scale_partials, int *zero_ints, int n_zero, cudaStream_t s) {
   constexpr int L = FwdRingLen<R>::L, NBLK = (V + L - 1) / L;
   const size_t smem = (size_t)V * kBwdThreads * sizeof(u64) + NBLK * sizeof(uint64_t);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(drc_blurz_bwd_fast_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
-    attr_done = true;
   }
   const int blocks = a.P * (V * V / 2) / kBwdThreads;
   drc_blurz_bwd_fast_kernel<V, R><<<blocks, kBwdThreads, smem, s>>>(

@@ -34,13 +34,23 @@ constexpr int kBwdThreads = 128;
 constexpr int kBwdPts = 4;
 int pose_partial_blocks(int N) { return (N + kBwdThreads * kBwdPts - 1) / (kBwdThreads * kBwdPts); }
 
+// The normalised quaternion of the CTA's projection, computed by ONE thread (a double-precision
+// square root and four IEEE divides: ~80 instructions that every thread would otherwise repeat)
+// and broadcast through shared memory.  Ends with a barrier: call it before any early return.
+__device__ __forceinline__ Quat block_quat(const float *__restrict__ q) {
+  __shared__ Quat sq;
+  if (threadIdx.x == 0) sq = load_quat(q);
+  __syncthreads();
+  return sq;
+}
+
 template <bool WRITE_TRPC, bool SCATTER>
 __global__ void __launch_bounds__(kPoseThreads)
 pose_scatter_kernel(PoseArgs a, float *__restrict__ tr_pc, float *__restrict__ grid) {
   const int b = blockIdx.y;
   const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  const Quat q = block_quat(a.quat + 4 * b);
   if (n >= a.N) return;
-  const Quat q = load_quat(a.quat + 4 * b);
   const bool has_t = a.trans != nullptr;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
   if (has_t) {
@@ -85,13 +95,13 @@ __global__ void __launch_bounds__(kPoseThreads)
 pose_cells_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
   const int b = blockIdx.y;
   const int n = blockIdx.x * kPoseThreads + threadIdx.x;
+  const Quat q = block_quat(a.quat + 4 * b);
   if (n >= cells.Npad) return;
   uint8_t *cz = cells.cellz + (size_t)b * cells.Npad;
   if (n >= a.N) {
     cz[n] = (uint8_t)kCellNone;
     return;
   }
-  const Quat q = load_quat(a.quat + 4 * b);
   const bool has_t = a.trans != nullptr;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
   if (has_t) {
@@ -371,7 +381,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
                        double *__restrict__ partials, int *__restrict__ counters, FinalizeArgs fin,
                        CellsView cells, const float4 *__restrict__ part) {
   const int b = blockIdx.y;
-  const Quat q = load_quat(a.quat + 4 * b);
+  const Quat q = block_quat(a.quat + 4 * b);
   const bool has_t = a.trans != nullptr;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
   if (has_t) {

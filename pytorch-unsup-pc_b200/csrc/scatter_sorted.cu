@@ -190,11 +190,10 @@ int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N
   sort_points_kernel<<<P, kSortThreads, 0, s>>>(src, a ? tr_pc_out : nullptr, bufA, bufB, N, Vz, V);
   if (int e = check_launch("sort_points")) return e;
   const size_t smem = (size_t)V * (kRowThreads + 1) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(segment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          128 * (kRowThreads + 1) * (int)sizeof(float));
-    attr_done = true;
   }
   dim3 g((Vz * V + kRowThreads - 1) / kRowThreads, P);
   segment_rows_kernel<<<g, kRowThreads, smem, s>>>(src, bufA, N, Vz, V, grid);
