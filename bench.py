@@ -50,7 +50,7 @@ WORKLOADS = {
               P=128, N=16000, V=128, K=21, sigma=3.0),
 }
 N_INPUT_SETS = 3          # distinct input sets rotated between steps
-E2E_GRAPH_STEPS = 12      # e2e steps captured per CUDA graph (a multiple of N_INPUT_SETS)
+E2E_GRAPH_STEPS = int(os.environ.get("DPC_E2E_GRAPH_STEPS", "24"))   # e2e steps captured per CUDA graph (a multiple of N_INPUT_SETS)
 
 
 def algorithmic_bytes(N, V, Vz):
@@ -224,6 +224,9 @@ def run_b200(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); "
                            "use --impl reference for the CPU arm")
     lib = _lib.load()
+    # one process per GPU: keep this rank (and the pinned staging buffers it allocates) on the
+    # GPU's own NUMA node
+    numa_cpus = dpc.bind_to_device_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -475,7 +478,9 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "no flush: %d input sets rotate and each step's grid + gradient-grid "
                          "working set (%d MiB) exceeds the 126 MB L2" % (
                              N_INPUT_SETS, 2 * P * Vz * V * V * 4 >> 20),
-                   "parallelism": "projections sharded across ranks, no collective"},
+                   "parallelism": "projections sharded across ranks, no collective",
+                   "host_binding": ("rank bound to the %d CPUs local to its GPU (NVML affinity)"
+                                    % len(numa_cpus)) if numa_cpus else "none"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                 "api": "pytorch_unsup_pc_b200.pointcloud_project_fast + torch.autograd.grad, "

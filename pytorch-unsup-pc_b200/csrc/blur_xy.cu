@@ -79,7 +79,10 @@ struct XYCfg {
   static constexpr bool ONE_TILE = (RH == V);
   static constexpr int TILE_LINES = ONE_TILE ? V / 2 : RH / 2 + V / 2;
   static constexpr size_t SMEM = (size_t)TILE_LINES * S * sizeof(float2);
-  static constexpr int MINB = V == 64 ? 9 : (V == 128 && RH == V ? 2 : 1);
+#ifndef DPC_XY_MINB64
+#define DPC_XY_MINB64 9
+#endif
+  static constexpr int MINB = V == 64 ? DPC_XY_MINB64 : (V == 128 && RH == V ? 2 : 1);
   static_assert(V % 32 == 0, "V must be a multiple of 32");
   static_assert(FILL_ITEMS % THREADS == 0, "fill loop must be warp-uniform");
   static_assert(!ONE_TILE || XTASKS == THREADS, "one-tile mode: one X task per thread");
@@ -216,6 +219,9 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       // clamp(raw, 0, 1) happens in the X pass, on the window loads
     }
     // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
+#ifdef DPC_XY_UNROLL_FILL
+#pragma unroll
+#endif
     for (int i = tid; i < ((POINTS && WRITE_BITS) ? 0 : C::FILL_ITEMS); i += C::THREADS) {
       const int rp = i / (V / 4), c4 = i % (V / 4);
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;

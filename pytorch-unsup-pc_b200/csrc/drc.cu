@@ -66,7 +66,10 @@ namespace dpc {
 #define DPC_FWD_L10 28
 #endif
 constexpr int kFwdThreads = 128;   // ray pairs per CTA (forward)
-constexpr int kBwdThreads = 64;    // ray pairs per CTA (backward: shared-memory bound)
+#ifndef DPC_BWD_THREADS
+#define DPC_BWD_THREADS 64
+#endif
+constexpr int kBwdThreads = DPC_BWD_THREADS;    // ray pairs per CTA (backward)
 
 int drc_scale_partial_blocks(int V) { return V * V / (2 * kBwdThreads); }
 
@@ -610,7 +613,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
         u64 a2 = pack2(fmaf(psi, gd.x, gm.x), fmaf(psi, gd.y, gm.y));
         if (j == 0 && k == 0) a2 = mul2(a2, ec2);
         float x0, x1, w0, w1;
-        unpack2(mul2(tseg[j], fma2(D2, neg2, a2)), x0, x1);            // T (a - D)
+        unpack2(mul2(tseg[j], fma2(D2, neg2, a2)), x0, x1);        // T (a - D)
         unpack2(w2, w0, w1);
         const u64 gv2 = pack2(w0 > 0.f ? x0 : 0.f, w1 > 0.f ? x1 : 0.f);   // sign bit = gate closed
         D2 = fma2(a2, v2, mul2(fma2(v2, neg2, one2), D2));             // D = a v + (1 - v) D
@@ -792,7 +795,8 @@ static void launch_bwd_fast(const DrcArgs &a, const RayConst &c, const Taps<R> &
                             const float *g_mask, const float *g_depth, float *g_grid,
                             float *scale_partials, int *zero_ints, int n_zero, cudaStream_t s) {
   constexpr int L = FwdRingLen<R>::L, NBLK = (V + L - 1) / L;
-  const size_t smem = (size_t)V * kBwdThreads * sizeof(u64) + NBLK * sizeof(uint64_t);
+  static_assert(NBLK * sizeof(uint64_t) <= 128, "mbarrier area");
+  const size_t smem = (size_t)V * kBwdThreads * sizeof(u64) + 128;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     cudaFuncSetAttribute(drc_blurz_bwd_fast_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -21,7 +21,39 @@ The kernels are untouched: this only orders copies and computation with CUDA
 events, and recycles ``depth`` sets of device input buffers so that no
 allocation or synchronisation happens in steady state.
 """
+import os
+
 import torch
+
+
+def bind_to_device_numa(device_index):
+    """Pin the calling process to the CPU cores local to GPU ``device_index`` (NVML's CPU
+    affinity of the device), so that pinned host buffers allocated afterwards -- and the copies
+    that read and write them -- stay on the GPU's own NUMA node.  With one process per GPU on a
+    two-socket host, an unbound rank whose staging buffers land on the far socket shares the
+    inter-socket link with every other rank's copies.  Returns the CPU set, or None when NVML or
+    the affinity call is unavailable (the process is left as it was)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            tag = ids[device_index]
+            handle = (pynvml.nvmlDeviceGetHandleByUUID(tag) if tag.startswith(("GPU-", "MIG-"))
+                      else pynvml.nvmlDeviceGetHandleByIndex(int(tag)))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 class HostPipeline:
