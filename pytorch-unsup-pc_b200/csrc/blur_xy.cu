@@ -57,6 +57,14 @@ __device__ __forceinline__ u64 bx_fma2(u64 a, u64 b, u64 c) {
   return d;
 }
 
+// Backward plane gather: planes touched by at most DPC_XY_SPARSE_Q / 4 points per thread evaluate
+// the last adjoint pass at the points only (0 = always the dense pass; A/B switch).  The sparse
+// pass trades 336 FFMA2 per thread for ~33 randomly addressed LDS.64 per point: measured faster at
+// 0.4 points per thread (workload B: 600 -> 489 us), slower at 1.6 (workload A: 44 -> 53 us).
+#ifndef DPC_XY_SPARSE_Q
+#define DPC_XY_SPARSE_Q 3
+#endif
+
 template <int V, int R>
 struct XYCfg {
   static constexpr int J = 16;                       // outputs per line per thread
@@ -285,6 +293,61 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   constexpr bool GATHER = POINTS && MASK_OUT;
   constexpr bool G_OVER_TILE = (C::YTASKS == C::THREADS);
   float *G = reinterpret_cast<float *>(G_OVER_TILE ? smem2 : smem2 + C::TILE_LINES * C::S);
+  if (GATHER && DPC_XY_SPARSE_Q > 0) {
+    // ---- sparse last pass: the Y adjoint only where a point needs it ----
+    // The backward consumes dL/draw at the 2 x 2 in-plane corners of the ~2N/Vz points that touch
+    // this plane and nowhere else.  The X pass above is dense (its input is); the Y pass is the
+    // LAST linear map before the gather, so it is evaluated at those corners only: 42 FFMA2 per
+    // touching point (rows iy and iy + 1 of columns ix, ix + 1 share one 22-deep window of the
+    // transposed tile) instead of 336 FFMA2 per thread.  Planes crowded with points (more than
+    // DPC_XY_SPARSE_Q / 4 per thread) take the dense pass below.
+    const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
+    const uint32_t *bs = cells.binstart + (size_t)pb * cells.zstride;
+    const uint32_t n_touch = __ldg(bs + pz + 1) - __ldg(bs + (pz > 0 ? pz - 1 : pz));
+    if (4 * n_touch <= (uint32_t)(DPC_XY_SPARSE_Q * C::THREADS)) {
+      const uint32_t *mb = bits_in + plane * (V * V / 32);
+      for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](const uint4 r, int dz) {
+        const int n = (int)(r.x >> 16), iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
+        const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
+        const bool y1 = iy + 1 < V, x1 = ix + 1 < V, odd = ix & 1;
+        const int cp0 = ix >> 1, cp1 = min(cp0 + 1, V / 2 - 1);
+        // window element i = X-blurred value of row iy - R + i (tile row index iy + i)
+        const float2 *c0 = B2 + cp0 * C::S + iy, *c1 = B2 + cp1 * C::S + iy;
+        u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;     // rows iy (a) and iy + 1 (b), two chains each
+#pragma unroll
+        for (int i = 0; i < 2 * R + 2; ++i) {
+          float2 lo = make_float2(0.f, 0.f), hi = lo;
+          if (i < 2 * R + 1 || y1) {             // element 2R+1 belongs to row iy + 1 only
+            lo = c0[i];
+            hi = c1[i];       // (loading it only for odd ix is slower: 489 -> 513 us, divergence)
+          }
+          const u64 ab = bx_pack2(odd ? lo.y : lo.x, odd ? hi.x : lo.y);   // (col ix, col ix + 1)
+          if (i < 2 * R + 1) { if (i & 1) a1 = bx_fma2(k2[i], ab, a1); else a0 = bx_fma2(k2[i], ab, a0); }
+          if (i > 0) { if (i & 1) b1 = bx_fma2(k2[i - 1], ab, b1); else b0 = bx_fma2(k2[i - 1], ab, b0); }
+        }
+        float G00, G01, G10, G11, t0, t1;
+        bx_unpack2(a0, G00, G01);
+        bx_unpack2(a1, t0, t1);
+        G00 += t0; G01 += t1;
+        bx_unpack2(b0, G10, G11);
+        bx_unpack2(b1, t0, t1);
+        G10 += t0; G11 += t1;
+        // the raw <= 1 gate of the clamp, and corners outside the grid carry no gradient
+        const int o0 = iy * V + ix, o1 = o0 + V;
+        const auto bit = [&](int o) { return (__ldg(mb + (o >> 5)) >> (o & 31)) & 1u; };
+        G00 = bit(o0) ? G00 : 0.f;
+        G01 = (x1 && bit(o0 + 1)) ? G01 : 0.f;
+        G10 = (y1 && bit(o1)) ? G10 : 0.f;
+        G11 = (y1 && x1 && bit(o1 + 1)) ? G11 : 0.f;
+        const float wz = dz ? rz : 1.f - rz, wy0 = 1.f - ry, wx0 = 1.f - rx;
+        const float sz = wy0 * (wx0 * G00 + rx * G01) + ry * (wx0 * G10 + rx * G11);
+        const float sy = wz * (wx0 * (G10 - G00) + rx * (G11 - G01));
+        const float sx = wz * (wy0 * (G01 - G00) + ry * (G11 - G10));
+        part[((size_t)dz * P + pb) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
+      });
+      return;
+    }
+  }
   for (int task = tid; task < C::YTASKS; task += C::THREADS) {
     const int cp = task % (V / 2), y0 = (task / (V / 2)) * C::J;
     u64 acc[C::J];
