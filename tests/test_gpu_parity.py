@@ -76,6 +76,60 @@ def test_golden_forward_and_gradients(dpc, name):
         assert v < FWD_TOL, (k, v)
     for k, v in gerrs.items():
         assert v < GRAD_TOL, (k, v)
+    # the same case without the optional outputs: the ray kernels then keep their fast saved
+    # state (signed clipped occupancy + transmittance checkpoints, one-sweep backward) wherever
+    # the grid is cubic and the DRC is in log-sum form
+    dpc.set_outputs(voxels=False, drc_probs=False)
+    try:
+        out2, loss2, grads2 = run_cuda(dpc, cfg, inp, P, V)
+    finally:
+        dpc.set_outputs(voxels=True, drc_probs=True)
+    assert out2["voxels"] is None and out2["drc_probs"] is None
+    for k in ("proj", "proj_depth", "tr_pc"):
+        assert _golden.rel_err(out2[k], rec[k]) < FWD_TOL, k
+    for k, g in grads2.items():
+        assert _golden.rel_err(g, rec["grad_" + k].reshape(g.shape)) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("outputs", [True, False])
+def test_half_batches_match_separate_calls(dpc, outputs):
+    """P >= 64 runs as two half-batches on two internal streams (dpc_project_chunks): every
+    projection must come out exactly as if its half had been projected alone -- bit for bit in
+    the deterministic mode, to scatter-order rounding otherwise -- in both saved-state layouts."""
+    dev = torch.device("cuda:0")
+    cfg = default_cfg(vox_size=32, pc_gauss_kernel_size=11)
+    P, N = 64, 700
+    case = _inputs.make_case(cfg, P, N, 4242, translation=True, scale=True, screened=False)
+    kern = CF.smoothing_taps(cfg, 1.5)
+    Wp, Wd = (w.to(dev) for w in _inputs.loss_weights(P, 32))
+
+    def run(sl):
+        leaves = [case[k][sl].to(dev).requires_grad_() for k in ("points", "quat", "translation", "scale")]
+        out = dpc.pointcloud_project_fast(cfg, leaves[0], leaves[1], leaves[2], None, kern,
+                                          scaling_factor=leaves[3])
+        loss = (out["proj"] * Wp[sl]).sum() + 0.1 * (out["proj_depth"] * Wd[sl]).sum()
+        return out, torch.autograd.grad(loss, leaves)
+
+    dpc.set_outputs(voxels=outputs, drc_probs=outputs)
+    try:
+        for det in (True, False):
+            dpc.set_deterministic(det)
+            whole, gw = run(slice(0, P))
+            for sl in (slice(0, P // 2), slice(P // 2, P)):
+                part, gp = run(sl)
+                for k in ("proj", "proj_depth", "tr_pc"):
+                    if det or k == "tr_pc":
+                        assert torch.equal(whole[k][sl], part[k]), (det, k)
+                    else:
+                        assert _golden.rel_err(whole[k][sl], part[k]) < FWD_TOL, (det, k)
+                for a, b in zip(gw, gp):
+                    if det:
+                        assert torch.equal(a[sl], b)
+                    else:
+                        assert _golden.rel_err(a[sl], b) < GRAD_TOL
+    finally:
+        dpc.set_deterministic(False)
+        dpc.set_outputs(voxels=True, drc_probs=True)
 
 
 @pytest.mark.parametrize("seed,sigma,kind", [(11, 3.0, "uniform"), (12, 0.7, "uniform"),
