@@ -80,7 +80,7 @@ NCU_TRAFFIC_BYTES = {
 
 
 def make_cfg(w):
-    from oracle.config import default_cfg
+    from pytorch_unsup_pc_b200.config import default_cfg
     return default_cfg(vox_size=w["V"], pc_gauss_kernel_size=w["K"])
 
 

@@ -6,6 +6,7 @@ names and signatures, hand-written sm_100a CUDA kernels behind a C ABI
 (include/dpc_b200.h).  Import as ``pytorch_unsup_pc_b200``.
 """
 from . import _lib
+from .config import Config, default_cfg
 from .gauss_kernel import gauss_kernel_1d, separable_kernels, smoothing_kernel
 from .point_cloud import (pc_perspective_transform, pointcloud2voxels3d_fast,
                           pointcloud_project_fast, smoothen_voxels3d, set_outputs,
@@ -24,7 +25,7 @@ __all__ = [
     "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "bind_to_device_numa", "add_proj_loss", "proj_loss_pose_candidates", "point_cloud_distance", "chamfer_distances",
     "pc_point_dropout", "pointcloud_project_replicated", "convolve_rgb",
     "project_volume_rgb_integral",
-    "library_path", "version",
+    "library_path", "version", "Config", "default_cfg",
 ]
 
 

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pytorch_unsup_pc_b200 as dpc
 from pytorch_unsup_pc_b200 import ops, _lib
-from oracle.config import default_cfg
+from pytorch_unsup_pc_b200.config import default_cfg
 
 def main(P=64, N=8000, V=64, K=21, sigma=3.0, iters=20):
     cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=K)
