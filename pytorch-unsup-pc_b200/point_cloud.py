@@ -205,10 +205,6 @@ def pointcloud_project_replicated(cfg, point_cloud, transform, predicted_transla
     ``keep_prob`` < 1 samples M = int(N * keep_prob) points per projection on the device;
     ``indices`` ([P,M], distinct per row) supplies the selection instead."""
     _check_quaternion_cfg(cfg)
-    if all_rgb is not None:
-        raise NotImplementedError("all_rgb: project the features with pointcloud_project_fast on "
-                                  "pc_point_dropout's outputs; the replica-aware entry point "
-                                  "carries no point features")
     if getattr(cfg, "ptn_max_projection", False):
         raise NotImplementedError("ptn_max_projection is broken in the reference "
                                   "(point_cloud_to.py:234,242) and not supported")
@@ -233,18 +229,29 @@ def pointcloud_project_replicated(cfg, point_cloud, transform, predicted_transla
     trans = ops._f32(predicted_translation, "predicted_translation", (P, 3))
     scale = _vec(scaling_factor, "scaling_factor", P)
     focal = _vec(focal_length, "focal_length", P)
+    col = None if all_rgb is None else _features(all_rgb, pts)      # [B,N,C], un-replicated too
     params = ops.make_params(cfg, P, N, flip_y=True)
+    taps = ops.host_taps(kernel)
     mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
-        pts, quat, trans, focal, scale, params, ops.host_taps(kernel),
-        _options["voxels"], _options["drc_probs"], _scatter_mode(), _options["plane_local"],
-        (P // B, N_src, sel))
+        pts, quat, trans, focal, scale, params, taps,
+        _options["voxels"], _options["drc_probs"] or col is not None, _scatter_mode(),
+        _options["plane_local"], (P // B, N_src, sel))
+    voxels_rgb = proj_rgb = None
+    if col is not None:
+        # the features of every projection's surviving points (they are C floats per point: this
+        # copy is the one replica tensor that does get materialised)
+        if sel is not None:
+            col = ops.SelectPointsFn.apply(col, sel, P // B)
+        else:
+            col = col.repeat_interleave(P // B, dim=0)
+        voxels_rgb, proj_rgb = _project_features(cfg, tr_pc, col.contiguous(), probs, taps, P, N)
     return {
         "proj": mask.unsqueeze(-1),
         "voxels": None if voxels is None else voxels.unsqueeze(-1),
         "tr_pc": tr_pc,
-        "voxels_rgb": None,
-        "proj_rgb": None,
-        "drc_probs": None if probs is None else probs.unsqueeze(-1),
+        "voxels_rgb": voxels_rgb,
+        "proj_rgb": proj_rgb,
+        "drc_probs": None if (probs is None or not _options["drc_probs"]) else probs.unsqueeze(-1),
         "proj_depth": depth.unsqueeze(-1),
         "dropout_indices": sel,
     }

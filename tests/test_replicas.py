@@ -99,9 +99,6 @@ def test_host_validation():
         dpc.pointcloud_project_replicated(cfg, torch.zeros(2, 10, 3), torch.zeros(4, 4), None, None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dpc.pc_point_dropout(torch.zeros(2, 10, 3), None, 0.5)
-    with pytest.raises(NotImplementedError):
-        dpc.pointcloud_project_replicated(cfg, torch.zeros(2, 10, 3), torch.zeros(4, 4), None,
-                                          torch.zeros(2, 10, 3))
 
 
 # ---------------------------------------------------------------------------- GPU
@@ -272,3 +269,38 @@ def test_replicated_with_device_dropout_full_size():
         assert _golden.rel_err(out["proj"], ref["proj"]) < 1e-5
     finally:
         dpc.set_outputs(voxels=True, drc_probs=True)
+
+
+@pytest.mark.gpu
+def test_replicated_with_point_features():
+    """Rows f2 and f3 together: un-replicated clouds AND un-replicated features, with dropout,
+    against the oracle on the materialised copies (forward 1e-5, gradients 1e-4)."""
+    import pytorch_unsup_pc_b200 as dpc
+    from oracle import rgb as ORGB
+    dev = torch.device("cuda:0")
+    cfg = default_cfg(vox_size=32, pc_gauss_kernel_size=11)
+    B, R, N, M = 2, 3, 600, 450
+    case = _inputs.make_case(cfg, B * R, N, 909, scale=True, screened=False)
+    g = torch.Generator().manual_seed(910)
+    cloud = case["points"][:B].contiguous()
+    feat = torch.rand(B, N, 3, generator=g)
+    sel = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(B * R)])
+    W = torch.rand(B * R, 32, 32, 3, generator=g)
+    kern = CF.smoothing_taps(cfg, 1.5)
+    for idx in (sel, None):
+        a, fa = cloud.clone().requires_grad_(), feat.clone().requires_grad_()
+        pts, col = OR.tf_repeat_0(a, R), OR.tf_repeat_0(fa, R)
+        if idx is not None:
+            pts, col = OR.pc_point_dropout(pts, col, _pairs(idx))
+        ref = ORGB.project_rgb(cfg, pts, case["quat"], col, None, kern, case["scale"])
+        gr = torch.autograd.grad((ref["proj_rgb"] * W.double()).sum() + ref["proj"].sum(), [a, fa])
+        b, fb = cloud.to(dev).requires_grad_(), feat.to(dev).requires_grad_()
+        out = dpc.pointcloud_project_replicated(cfg, b, case["quat"].to(dev), None, fb, kern,
+                                                scaling_factor=case["scale"].to(dev),
+                                                indices=None if idx is None else idx.to(dev))
+        gc = torch.autograd.grad((out["proj_rgb"] * W.to(dev)).sum() + out["proj"].sum(), [b, fb])
+        assert _golden.rel_err(out["proj_rgb"], ref["proj_rgb"]) < 1e-5
+        assert _golden.rel_err(out["proj"], ref["proj"]) < 1e-5
+        assert gc[0].shape == cloud.shape and gc[1].shape == feat.shape
+        for x, y in zip(gc, gr):
+            assert _golden.rel_err(x, y) < 1e-4
