@@ -67,7 +67,10 @@ __device__ __forceinline__ u64 bx_fma2(u64 a, u64 b, u64 c) {
 
 template <int V, int R>
 struct XYCfg {
-  static constexpr int J = 16;                       // outputs per line per thread
+#ifndef DPC_XY_J
+#define DPC_XY_J 16
+#endif
+  static constexpr int J = DPC_XY_J;                 // outputs per line per thread
   static constexpr int W = J + 2 * R;                // window positions (even)
   static constexpr int W2 = W / 2;                   // LDS.128 per window
 #ifndef DPC_XY_RH128
@@ -80,7 +83,7 @@ struct XYCfg {
   static constexpr int S = (S0 % 4 == 2) ? S0 : S0 + 2;   // stride in pairs, S/2 odd
   static constexpr int XTASKS = (RH / 2) * (V / J);
   static constexpr int YTASKS = (V / 2) * (V / J);
-  static constexpr int THREADS = YTASKS < 128 ? YTASKS : (V == 128 ? (RH == V ? 512 : 256) : 128);
+  static constexpr int THREADS = (RH == V) ? XTASKS : (YTASKS < 128 ? YTASKS : (V == 128 ? 256 : 128));
   static constexpr int FILL_ITEMS = (RH / 2) * (V / 4);
   // V <= 64: the X-pass results wait in registers while the tile is reused for
   // the transposed layout, so one tile suffices (22 KB -> 9-10 CTAs per SM)
@@ -117,7 +120,11 @@ __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, cons
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int t = 2 * i + c - j;  // compile-time after unrolling
+#ifdef DPC_PROBE_FEW_FMA
+        if (t == R) acc[j] = bx_fma2(k2[t], vv[c], acc[j]);     // timing probe: 1 tap of 2R+1
+#else
         if (t >= 0 && t <= 2 * R) acc[j] = bx_fma2(k2[t], vv[c], acc[j]);
+#endif
       }
     }
   }
@@ -136,14 +143,30 @@ __device__ __forceinline__ float4 clamp01(float4 v) {
 // dz = 1 when it is the upper one (iz == z - 1, weight rz).  The records are
 // sorted by z cell (bin_points_kernel), so the ~2N/Vz touching points are ONE
 // contiguous range: coalesced 16-byte loads, no scan, every lane busy.
-template <typename F>
-__device__ __forceinline__ void for_each_touching_point(const CellsView &cells, int b, int z,
-                                                        int N, int tid, int nthreads, F &&f) {
+struct TouchRange {
+  uint32_t lo, mid, hi;     // srec[lo, mid): cell iz == z - 1 (dz = 1); srec[mid, hi): iz == z (dz = 0)
+  const uint4 *srec;
+};
+__device__ __forceinline__ TouchRange touch_range(const CellsView &cells, int b, int z, int N) {
   const uint32_t *bs = cells.binstart + (size_t)b * cells.zstride;
-  const uint32_t mid = __ldg(bs + z), hi = __ldg(bs + z + 1);
-  const uint32_t lo = z > 0 ? __ldg(bs + z - 1) : mid;
-  const uint4 *srec = cells.srec + (size_t)b * N;
-  for (uint32_t i = lo + tid; i < hi; i += nthreads) f(__ldg(srec + i), i < mid ? 1 : 0);
+  TouchRange t;
+  t.mid = __ldg(bs + z);
+  t.hi = __ldg(bs + z + 1);
+  t.lo = z > 0 ? __ldg(bs + z - 1) : t.mid;
+  t.srec = cells.srec + (size_t)b * N;
+  return t;
+}
+// `first`: this thread's first record, loaded by the caller ahead of time (right after the range,
+// before the work that precedes the scatter / gather), so its latency is off the critical path
+template <typename F>
+__device__ __forceinline__ void for_each_touching_point(const TouchRange &t, int tid, int nthreads,
+                                                        const uint4 first, F &&f) {
+  uint32_t i = t.lo + tid;
+  if (i < t.hi) f(first, i < t.mid ? 1 : 0);
+  for (i += nthreads; i < t.hi; i += nthreads) f(__ldg(t.srec + i), i < t.mid ? 1 : 0);
+}
+__device__ __forceinline__ uint4 first_touching_record(const TouchRange &t, int tid) {
+  return t.lo + tid < t.hi ? __ldg(t.srec + t.lo + tid) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Shared-memory float add that returns the NEW value (fp32 shared atomics are a
@@ -181,9 +204,36 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   const size_t plane = blockIdx.x;
   const float *sp = src + plane * V * V;
 
-  // zero both tiles once (the pads stay zero for the whole kernel)
-  for (int i = tid; i < C::TILE_LINES * C::S / 2; i += C::THREADS)
-    reinterpret_cast<float4 *>(smem2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the points touching this plane: the range now, the thread's first record right behind it --
+  // both are in flight while the tile is zeroed (forward) / filled and blurred (backward)
+  const int pb = POINTS ? (int)(plane / Vz) : 0, pz = POINTS ? (int)(plane - (size_t)pb * Vz) : 0;
+  TouchRange touch = {0u, 0u, 0u, nullptr};
+  uint4 rec0 = make_uint4(0u, 0u, 0u, 0u);
+#ifndef DPC_XY_PREFETCH
+#define DPC_XY_PREFETCH 1
+#endif
+#ifndef DPC_XY_PADZERO
+#define DPC_XY_PADZERO 1
+#endif
+  if (POINTS && DPC_XY_PREFETCH) {
+    touch = touch_range(cells, pb, pz, N);
+    rec0 = first_touching_record(touch, tid);
+  }
+  // (pads only: measured 498 -> 484 us at 128^2, but 43.0 -> 46.7 us at 64^2, where the whole
+  // tile is 11 vector stores per thread)
+  if ((POINTS && WRITE_BITS) || !DPC_XY_PADZERO || V < 128) {
+    // the scatter accumulates into the tile: all of it starts at zero
+    for (int i = tid; i < C::TILE_LINES * C::S / 2; i += C::THREADS)
+      reinterpret_cast<float4 *>(smem2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    // the interior is overwritten by the fill (and by the transposed X-pass results): only the
+    // R-wide zero pads of every line need clearing
+    constexpr int PADP = C::S - V;
+    for (int i = tid; i < C::TILE_LINES * PADP; i += C::THREADS) {
+      const int line = i / PADP, k = i - line * PADP;
+      smem2[line * C::S + (k < R ? k : V + k)] = make_float2(0.f, 0.f);
+    }
+  }
   u64 k2[2 * R + 1];
 #pragma unroll
   for (int t = 0; t < 2 * R + 1; ++t) k2[t] = bx_pack2(kx.k[t], kx.k[t]);
@@ -193,7 +243,6 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   for (int h = 0; h < V / C::RH; ++h) {
     if (POINTS && WRITE_BITS) {
       // ---- build rows [h*RH, (h+1)*RH) of the raw plane from the touching points ----
-      const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
       if (h > 0) {
         for (int i = tid; i < HALF * C::S / 2; i += C::THREADS)
           reinterpret_cast<float4 *>(A2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -205,7 +254,12 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       uint32_t *sbits = reinterpret_cast<uint32_t *>(smem2 + C::TILE_LINES * C::S);
       for (int i = tid; i < C::RH * V / 32; i += C::THREADS) sbits[i] = 0xffffffffu;
       __syncthreads();
-      for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](const uint4 r, int dz) {
+#ifndef DPC_PROBE_NO_SCATTER
+      if (!DPC_XY_PREFETCH) {
+        touch = touch_range(cells, pb, pz, N);
+        rec0 = first_touching_record(touch, tid);
+      }
+      for_each_touching_point(touch, tid, C::THREADS, rec0, [&](const uint4 r, int dz) {
         const int iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
         const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
         const float wz = dz ? rz : 1.f - rz;
@@ -221,6 +275,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
             atomicAnd(sbits + (lr * V + ix + 1) / 32, ~(1u << ((ix + 1) & 31)));
         }
       });
+#endif
       __syncthreads();
       for (int i = tid; i < C::RH * V / 32; i += C::THREADS)
         bits_out[plane * (V * V / 32) + h * (C::RH * V / 32) + i] = sbits[i];
@@ -233,8 +288,12 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     for (int i = tid; i < ((POINTS && WRITE_BITS) ? 0 : C::FILL_ITEMS); i += C::THREADS) {
       const int rp = i / (V / 4), c4 = i % (V / 4);
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;
+#ifdef DPC_PROBE_NO_FILL
+      float4 a = make_float4(0.f, 1.f, 0.f, 1.f), b = a;
+#else
       float4 a = __ldg(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
       float4 b = __ldg(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
+#endif
       if (WRITE_BITS) {
         uint32_t na = le1_nibble(a) << (4 * (tid & 7)), nb = le1_nibble(b) << (4 * (tid & 7));
 #pragma unroll
@@ -293,6 +352,10 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   constexpr bool GATHER = POINTS && MASK_OUT;
   constexpr bool G_OVER_TILE = (C::YTASKS == C::THREADS);
   float *G = reinterpret_cast<float *>(G_OVER_TILE ? smem2 : smem2 + C::TILE_LINES * C::S);
+  if (GATHER && !DPC_XY_PREFETCH) {
+    touch = touch_range(cells, pb, pz, N);
+    rec0 = first_touching_record(touch, tid);
+  }
   if (GATHER && DPC_XY_SPARSE_Q > 0) {
     // ---- sparse last pass: the Y adjoint only where a point needs it ----
     // The backward consumes dL/draw at the 2 x 2 in-plane corners of the ~2N/Vz points that touch
@@ -301,12 +364,10 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     // touching point (rows iy and iy + 1 of columns ix, ix + 1 share one 22-deep window of the
     // transposed tile) instead of 336 FFMA2 per thread.  Planes crowded with points (more than
     // DPC_XY_SPARSE_Q / 4 per thread) take the dense pass below.
-    const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
-    const uint32_t *bs = cells.binstart + (size_t)pb * cells.zstride;
-    const uint32_t n_touch = __ldg(bs + pz + 1) - __ldg(bs + (pz > 0 ? pz - 1 : pz));
+    const uint32_t n_touch = touch.hi - touch.lo;
     if (4 * n_touch <= (uint32_t)(DPC_XY_SPARSE_Q * C::THREADS)) {
       const uint32_t *mb = bits_in + plane * (V * V / 32);
-      for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](const uint4 r, int dz) {
+      for_each_touching_point(touch, tid, C::THREADS, rec0, [&](const uint4 r, int dz) {
         const int n = (int)(r.x >> 16), iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
         const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
         const bool y1 = iy + 1 < V, x1 = ix + 1 < V, odd = ix & 1;
@@ -357,22 +418,24 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     for (int j = 0; j < C::J; ++j) {
       float lo, hi;
       bx_unpack2(acc[j], lo, hi);
+#ifndef DPC_PROBE_NO_MASK
       if (MASK_OUT) {
         const uint32_t wbits = __ldg(bits_in + plane * (V * V / 32) + ((y0 + j) * V + 2 * cp) / 32);
         const uint32_t sh = (2 * cp) & 31;
         lo = ((wbits >> sh) & 1u) ? lo : 0.f;
         hi = ((wbits >> (sh + 1)) & 1u) ? hi : 0.f;
       }
+#endif
       if (GATHER)
         *reinterpret_cast<float2 *>(G + (y0 + j) * V + 2 * cp) = make_float2(lo, hi);
       else
         *reinterpret_cast<float2 *>(dp + (y0 + j) * V + 2 * cp) = make_float2(lo, hi);
     }
   }
+#ifndef DPC_PROBE_NO_GATHER
   if (GATHER) {
     __syncthreads();
-    const int pb = (int)(plane / Vz), pz = (int)(plane - (size_t)pb * Vz);
-    for_each_touching_point(cells, pb, pz, N, tid, C::THREADS, [&](const uint4 r, int dz) {
+    for_each_touching_point(touch, tid, C::THREADS, rec0, [&](const uint4 r, int dz) {
       const int n = (int)(r.x >> 16), iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
       const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
       const bool y1 = iy + 1 < V, x1 = ix + 1 < V;   // out-of-range corners carry no gradient
@@ -387,6 +450,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       part[((size_t)dz * P + pb) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
     });
   }
+#endif
 }
 
 template <int V, int R>
