@@ -400,8 +400,9 @@ static bool plane_local_ok(const dpc_params *p) {
 
 // The DRC kernels' fast saved state (drc.cu): decided from what BOTH passes know.
 static bool fast_ray_state(const dpc_params *p, const void *cells, int scatter_mode) {
+  // (clip value > 0: the saved v >= clip is then strictly positive and its sign bit is free)
   return cells && scatter_mode == DPC_SCATTER_ATOMIC && p->Vz == p->V && p->outputs == 0 &&
-         p->drc_logsum != 0;
+         p->drc_logsum != 0 && p->drc_clip > 0.0 && p->drc_clip < 0.5;
 }
 static void set_ray_state(DrcArgs &da, const dpc_params *p, void *cells, int b0) {
   da.ck_slots = ray_ck_slots(p->Vz);
