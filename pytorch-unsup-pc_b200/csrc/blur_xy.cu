@@ -100,7 +100,10 @@ struct XYCfg {
 };
 
 // 16 packed outputs from a window of W pair-positions starting at `win`
-template <int R, int J, int W2, bool MIN1 = false>
+// IN: how a window element becomes the value to blur: 0 as stored; 1 clamp(raw, 0, 1) of a
+// non-negative raw value = min(v, 1); 2 the plane scatter's biased fixed point (see
+// scatter_add_fixed): the tile holds 1 + raw, so clamp(raw, 0, 1) = min(v, 2) - 1, exactly
+template <int R, int J, int W2, int IN = 0>
 __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, const u64 (&k2)[2 * R + 1],
                                             u64 (&acc)[J]) {
 #pragma unroll
@@ -108,11 +111,16 @@ __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, cons
 #pragma unroll
   for (int i = 0; i < W2; ++i) {
     float4 v4 = *reinterpret_cast<const float4 *>(win + 2 * i);
-    if (MIN1) {   // clamp(raw, 0, 1) of a non-negative raw value, taken on the way in
+    if (IN == 1) {
       v4.x = fminf(v4.x, 1.f);
       v4.y = fminf(v4.y, 1.f);
       v4.z = fminf(v4.z, 1.f);
       v4.w = fminf(v4.w, 1.f);
+    } else if (IN == 2) {
+      v4.x = fminf(v4.x, 2.f) - 1.f;
+      v4.y = fminf(v4.y, 2.f) - 1.f;
+      v4.z = fminf(v4.z, 2.f) - 1.f;
+      v4.w = fminf(v4.w, 2.f) - 1.f;
     }
     const u64 vv[2] = {bx_pack2(v4.x, v4.y), bx_pack2(v4.z, v4.w)};
 #pragma unroll
@@ -183,6 +191,23 @@ __device__ __forceinline__ float smem_add_new(float *p, float w) {
   return nv;
 }
 
+// Plane scatter in BIASED FIXED POINT.  A tile element starts as the float 1.0f; adding the
+// integer round(w * 2^23) to its BIT PATTERN adds w (quantised to 2^-23 = 1.2e-7) to the float
+// it spells, exactly, as long as the value stays in [1, 2] -- i.e. while raw <= 1, the only range
+// whose value matters (clamp(raw, 0, 1) follows).  That turns the accumulation into the native
+// shared-memory integer atomic (ATOMS.ADD, four independent ones in flight per point) instead of
+// four serial compare-and-swap loops, and integer adds commute: the plane no longer depends on
+// the order in which points arrive, so the default path is bit-reproducible run to run.
+// raw > 1  <=>  bits > bits(2.0f) (positive floats order like their bit patterns); elements that
+// are already past 2.0 are left alone, which bounds the sum far below the next binade overflow.
+constexpr uint32_t kFixOne = 0x3F800000u, kFixTwo = 0x40000000u;
+__device__ __forceinline__ bool scatter_add_fixed(float *p, float w) {   // true: element now > 1
+  uint32_t *ip = reinterpret_cast<uint32_t *>(p);
+  if (*reinterpret_cast<volatile uint32_t *>(ip) > kFixTwo) return false;   // saturated before
+  const uint32_t wq = __float2uint_rn(w * 8388608.f);
+  return atomicAdd(ip, wq) + wq > kFixTwo;
+}
+
 __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
   return (v.x <= 1.f ? 1u : 0u) | (v.y <= 1.f ? 2u : 0u) | (v.z <= 1.f ? 4u : 0u) |
          (v.w <= 1.f ? 8u : 0u);
@@ -221,10 +246,17 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   }
   // (pads only: measured 498 -> 484 us at 128^2, but 43.0 -> 46.7 us at 64^2, where the whole
   // tile is 11 vector stores per thread)
+#ifndef DPC_XY_FIXED
+#define DPC_XY_FIXED 1
+#endif
+  // fixed-point plane scatter (one-tile layouts): the tile starts as the bias 1.0f, pads included,
+  // so that the X pass decodes every window element alike; the pads are zeroed for the Y pass
+  constexpr bool FIXED = POINTS && WRITE_BITS && C::ONE_TILE && DPC_XY_FIXED;
   if ((POINTS && WRITE_BITS) || !DPC_XY_PADZERO || V < 128) {
-    // the scatter accumulates into the tile: all of it starts at zero
+    // the scatter accumulates into the tile: all of it starts at zero (at the bias when FIXED)
+    const float z0 = FIXED ? 1.f : 0.f;
     for (int i = tid; i < C::TILE_LINES * C::S / 2; i += C::THREADS)
-      reinterpret_cast<float4 *>(smem2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4 *>(smem2)[i] = make_float4(z0, z0, z0, z0);
   } else {
     // the interior is overwritten by the fill (and by the transposed X-pass results): only the
     // R-wide zero pads of every line need clearing
@@ -269,9 +301,11 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
           if (iy + dy >= V || lr < 0 || lr >= C::RH) continue;
           const float wzy = wz * (dy ? ry : 1.f - ry);
           float *cellp = reinterpret_cast<float *>(A2 + (lr % HALF) * C::S + R + ix) + lr / HALF;
-          if (smem_add_new(cellp, wzy * (1.f - rx)) > 1.f)
+          if (FIXED ? scatter_add_fixed(cellp, wzy * (1.f - rx))
+                    : smem_add_new(cellp, wzy * (1.f - rx)) > 1.f)
             atomicAnd(sbits + (lr * V + ix) / 32, ~(1u << (ix & 31)));
-          if (ix + 1 < V && smem_add_new(cellp + 2, wzy * rx) > 1.f)
+          if (ix + 1 < V && (FIXED ? scatter_add_fixed(cellp + 2, wzy * rx)
+                                   : smem_add_new(cellp + 2, wzy * rx) > 1.f))
             atomicAnd(sbits + (lr * V + ix + 1) / 32, ~(1u << ((ix + 1) & 31)));
         }
       });
@@ -326,8 +360,16 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     for (int task = tid; task < C::XTASKS; task += C::THREADS) {
       const int rp = task % HALF, x0 = (task / HALF) * C::J;
       u64 acc[C::J];
-      window_fma2<R, C::J, C::W2, POINTS && WRITE_BITS>(A2 + rp * C::S + x0, k2, acc);
+      window_fma2<R, C::J, C::W2, FIXED ? 2 : (POINTS && WRITE_BITS ? 1 : 0)>(A2 + rp * C::S + x0,
+                                                                               k2, acc);
       if (C::ONE_TILE) __syncthreads();   // every window is in registers: the tile can be reused
+      if (FIXED) {                        // the pads held the bias: zero padding for the Y pass
+        constexpr int PADP = C::S - V;
+        for (int i = tid; i < C::TILE_LINES * PADP; i += C::THREADS) {
+          const int line = i / PADP, k = i - line * PADP;
+          smem2[line * C::S + (k < R ? k : V + k)] = make_float2(0.f, 0.f);
+        }
+      }
       // acc[j] = (out[r0][x0+j], out[r1][x0+j]) -> B2[(x0+j)/2][R + row] = (even col, odd col)
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;
       float2 *b = B2 + (x0 / 2) * C::S + R;

@@ -91,6 +91,23 @@ def test_golden_forward_and_gradients(dpc, name):
         assert _golden.rel_err(g, rec["grad_" + k].reshape(g.shape)) < GRAD_TOL, k
 
 
+@pytest.mark.parametrize("kind", ["uniform", "clustered"])
+def test_default_path_is_reproducible(dpc, kind):
+    """The plane scatter accumulates in biased fixed point with integer atomics (order-free) and
+    every reduction of the backward runs in a fixed order: the DEFAULT path returns the same bits
+    run after run, pile-ups included."""
+    cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
+    case = _inputs.make_case(cfg, 4, 8000, 515, kind=kind, translation=True, screened=False)
+    case["points"][3, :3000] = case["points"][3, 0]           # 3000 points in ONE cell
+    case["kernel"] = CF.smoothing_taps(cfg, 3.0)
+    runs = [run_cuda(dpc, cfg, case, 4, 64) for _ in range(3)]
+    for out, loss, grads in runs[1:]:
+        for k in ("proj", "proj_depth", "voxels", "drc_probs", "tr_pc"):
+            assert torch.equal(out[k], runs[0][0][k]), k
+        for k in grads:
+            assert torch.equal(grads[k], runs[0][2][k]), k
+
+
 @pytest.mark.parametrize("outputs", [True, False])
 def test_half_batches_match_separate_calls(dpc, outputs):
     """P >= 64 runs as two half-batches on two internal streams (dpc_project_chunks): every
