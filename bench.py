@@ -344,52 +344,62 @@ def run_b200(args, rank, world, local_rank):
     # ---- (2) e2e: public Python API, pinned host inputs in, results out, every step ----
     dpc.set_outputs(voxels=False, drc_probs=False)
     dpc.point_cloud._options["plane_local"] = not args.global_grid
-    out_host = dict(mask=torch.empty(P, V, V, 1).pin_memory(), depth=torch.empty(P, V, V, 1).pin_memory(),
-                    g_points=torch.empty(P, N, 3).pin_memory(), g_quat=torch.empty(P, 4).pin_memory(),
-                    g_scale=torch.empty(P, 1).pin_memory())
-    h2d = sum(host[0][k].numel() * 4 for k in ("points", "quat", "scale"))
-    d2h = sum(v.numel() * 4 for v in out_host.values())
+    E2E_LANES = int(os.environ.get("DPC_E2E_LANES", "2"))
 
-    pipe = dpc.HostPipeline(dev, depth=3)
+    def make_e2e(project, host_sets, out_shapes, nbytes_in, nbytes_out):
+        """lane -> step function: this step's inputs pinned host memory -> device (copy stream,
+        overlapped with the previous step's kernels); results and gradients device -> pinned host
+        memory (readback stream, overlapped with the next step's kernels).  Every lane has its
+        own pipeline and its own pinned result buffers."""
+        def make_step(lane, pipe):
+            out_h = {k: torch.empty(*shp).pin_memory() for k, shp in out_shapes.items()}
 
-    def step_e2e(i):
-        # this step's inputs: pinned host memory -> device (copy stream, overlapped with the
-        # previous step's kernels); results and gradients: device -> pinned host memory
-        # (readback stream, overlapped with the next step's kernels)
-        h = host[i % N_INPUT_SETS]
-        din = pipe.upload({"points": h["points"], "quat": h["quat"], "scale": h["scale"]})
-        pts = din["points"].detach().requires_grad_()
-        quat = din["quat"].detach().requires_grad_()
-        scale = din["scale"].detach().requires_grad_()
-        d = devin[i % N_INPUT_SETS]
-        out = dpc.pointcloud_project_fast(cfg, pts, quat, None, None, kern, scaling_factor=scale)
-        gp, gq, gs = torch.autograd.grad([out["proj"], out["proj_depth"]], [pts, quat, scale],
-                                         [d["g_mask"], d["g_depth"]])
-        pipe.download({"mask": out["proj"], "depth": out["proj_depth"], "g_points": gp,
-                       "g_quat": gq, "g_scale": gs}, out_host)
-        assert pipe.h2d_bytes == h2d and pipe.d2h_bytes == d2h
+            def step(i):
+                h = host_sets[i % N_INPUT_SETS]
+                din = pipe.upload({"points": h["points"], "quat": h["quat"], "scale": h["scale"]})
+                pts = din["points"].detach().requires_grad_()
+                quat = din["quat"].detach().requires_grad_()
+                scale = din["scale"].detach().requires_grad_()
+                d = devin[i % N_INPUT_SETS]
+                out = project(cfg, pts, quat, None, None, kern, scaling_factor=scale)
+                gp, gq, gs = torch.autograd.grad([out["proj"], out["proj_depth"]], [pts, quat, scale],
+                                                 [d["g_mask"], d["g_depth"]])
+                pipe.download({"mask": out["proj"], "depth": out["proj_depth"], "g_points": gp,
+                               "g_quat": gq, "g_scale": gs}, out_h)
+                assert pipe.h2d_bytes == nbytes_in and pipe.d2h_bytes == nbytes_out
+            return step
+        return make_step
 
-    def measure_e2e(step_fn):
+    def measure_e2e(make_step):
         if args.graph:
             # E2E_GRAPH_STEPS consecutive e2e steps (each with its own H2D and D2H copies) captured
-            # once with the public GraphedSteps helper and replayed: the eager loop is bound by
-            # the host (~0.35 ms of Python / autograd-engine work per ~0.2 ms step)
-            gs = dpc.GraphedSteps(step_fn, E2E_GRAPH_STEPS, dev, pipe=pipe, warmup=2)
+            # once per lane with the public helpers and replayed: the eager loop is bound by the
+            # host (~0.25 ms of Python / autograd-engine work per ~0.15 ms step); two lanes
+            # replayed in turn keep the copy pipeline from draining at every replay boundary
+            ag = dpc.AlternatingGraphs(make_step, E2E_GRAPH_STEPS, dev, lanes=E2E_LANES, warmup=2)
             reps = (args.steps + E2E_GRAPH_STEPS - 1) // E2E_GRAPH_STEPS
+            reps += reps % E2E_LANES and (E2E_LANES - reps % E2E_LANES)
 
             def replay_e2e(i):
                 if i % E2E_GRAPH_STEPS == 0:
-                    gs.replay()
-            ms = timed(replay_e2e, reps * E2E_GRAPH_STEPS, 2 * E2E_GRAPH_STEPS) * args.steps / (
-                reps * E2E_GRAPH_STEPS)
-            mode = "GraphedSteps(%d steps per CUDA graph)" % E2E_GRAPH_STEPS
+                    ag.replay()
+            ms = timed(replay_e2e, reps * E2E_GRAPH_STEPS, 2 * E2E_LANES * E2E_GRAPH_STEPS,
+                       join=ag.streams) * args.steps / (reps * E2E_GRAPH_STEPS)
+            mode = "AlternatingGraphs(%d lanes x %d steps per CUDA graph)" % (E2E_LANES, E2E_GRAPH_STEPS)
+            for p_ in ag.pipes:
+                p_.drain()
         else:
-            ms = timed(step_fn, args.steps, max(args.warmup, 3), join=(pipe.h2d, pipe.d2h))
+            pipe = dpc.HostPipeline(dev, depth=3)
+            ms = timed(make_step(0, pipe), args.steps, max(args.warmup, 3), join=(pipe.h2d, pipe.d2h))
             mode = "eager"
-        pipe.drain()
+            pipe.drain()
         return ms, mode
 
-    ms_e2e, e2e_mode = measure_e2e(step_e2e)
+    out_shapes = dict(mask=(P, V, V, 1), depth=(P, V, V, 1), g_points=(P, N, 3), g_quat=(P, 4),
+                      g_scale=(P, 1))
+    h2d = sum(host[0][k].numel() * 4 for k in ("points", "quat", "scale"))
+    d2h = sum(4 * int(torch.Size(shp).numel()) for shp in out_shapes.values())
+    ms_e2e, e2e_mode = measure_e2e(make_e2e(dpc.pointcloud_project_fast, host, out_shapes, h2d, d2h))
 
     # ---- (2b) the same step through the replica-aware API (next row f2): the host holds the
     # UN-replicated clouds (P / candidates of them), the kernels read cloud b // candidates, and
@@ -400,33 +410,17 @@ def run_b200(args, rank, world, local_rank):
         B = P // R
         host_rep = [{"points": h["points"][::R].contiguous().pin_memory(), "quat": h["quat"],
                      "scale": h["scale"]} for h in host]
-        out_host_rep = dict(out_host, g_points=torch.empty(B, N, 3).pin_memory())
+        shapes_rep = dict(out_shapes, g_points=(B, N, 3))
         h2d_rep = sum(host_rep[0][k].numel() * 4 for k in ("points", "quat", "scale"))
-        d2h_rep = sum(v.numel() * 4 for v in out_host_rep.values())
-
-        def step_e2e_rep(i):
-            h = host_rep[i % N_INPUT_SETS]
-            din = pipe.upload({"points": h["points"], "quat": h["quat"], "scale": h["scale"]})
-            pts = din["points"].detach().requires_grad_()
-            quat = din["quat"].detach().requires_grad_()
-            scale = din["scale"].detach().requires_grad_()
-            d = devin[i % N_INPUT_SETS]
-            out = dpc.pointcloud_project_replicated(cfg, pts, quat, None, None, kern,
-                                                    scaling_factor=scale)
-            gp, gq, gs = torch.autograd.grad([out["proj"], out["proj_depth"]], [pts, quat, scale],
-                                             [d["g_mask"], d["g_depth"]])
-            pipe.download({"mask": out["proj"], "depth": out["proj_depth"], "g_points": gp,
-                           "g_quat": gq, "g_scale": gs}, out_host_rep)
-            assert pipe.h2d_bytes == h2d_rep and pipe.d2h_bytes == d2h_rep
-
-        ms_rep, mode_rep = measure_e2e(step_e2e_rep)
+        d2h_rep = sum(4 * int(torch.Size(shp).numel()) for shp in shapes_rep.values())
+        ms_rep, mode_rep = measure_e2e(make_e2e(dpc.pointcloud_project_replicated, host_rep,
+                                                shapes_rep, h2d_rep, d2h_rep))
         e2e_rep = {"value": world * P * args.steps / (ms_rep * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": h2d_rep, "d2h_bytes_per_step": d2h_rep,
                    "ms_per_step": ms_rep / args.steps,
                    "api": "pytorch_unsup_pc_b200.pointcloud_project_replicated: %d clouds x %d pose "
                           "candidates per step, cloud gradient summed over the candidates in the "
                           "kernels" % (B, R), "mode": mode_rep}
-    pipe.drain()
     # ---- (3) per-stage CUDA-event timings for the roofline ----
     stage_ms = (ctypes.c_float * len(_lib.PROFILE_STAGES))()
     d = devin[0]
@@ -485,7 +479,8 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                 "api": "pytorch_unsup_pc_b200.pointcloud_project_fast + torch.autograd.grad, "
                        "host copies through pytorch_unsup_pc_b200.HostPipeline (3 streams: this "
-                       "step's H2D / kernels / D2H overlap the neighbouring steps')",
+                       "step's H2D / kernels / D2H overlap the neighbouring steps'), steps "
+                       "captured and replayed with pytorch_unsup_pc_b200.AlternatingGraphs",
                 "mode": e2e_mode},
         "e2e_replica_aware": e2e_rep,
         # kernels per chunk: pose_cells + bin_points (or pose_scatter), blur_xy, blurz_drc_fwd |

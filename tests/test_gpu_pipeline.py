@@ -97,3 +97,57 @@ def test_graphed_steps_replay_matches_eager():
         for n in r:
             assert torch.equal(r[n], h[n]), n
     assert not torch.equal(ref[0]["mask"], ref2[0]["mask"])
+
+
+def test_alternating_graphs_match_eager():
+    """Two lanes of captured steps replayed in turn on two streams: every lane's host results equal
+    the eager loop's, replay after replay."""
+    import pytorch_unsup_pc_b200 as dpc
+    dev = torch.device("cuda:0")
+    cfg = default_cfg(vox_size=32, pc_gauss_kernel_size=11)
+    kern = dpc.smoothing_kernel(cfg, 1.5)
+    P, N, V, S, L = 4, 1500, 32, 3, 2
+    g = torch.Generator().manual_seed(19)
+    stage = [[{"points": ((torch.rand(P, N, 3, generator=g) - 0.5) * 0.9).pin_memory(),
+               "quat": torch.randn(P, 4, generator=g).pin_memory()} for _ in range(S)] for _ in range(L)]
+    host = [[{"mask": torch.zeros(P, V, V, 1).pin_memory(), "g_points": torch.zeros(P, N, 3).pin_memory()}
+             for _ in range(S)] for _ in range(L)]
+    w = torch.rand(P, V, V, 1, generator=g).to(dev)
+
+    def make_step(lane, pipe):
+        def step(k):
+            d = pipe.upload(stage[lane][k])
+            pts = d["points"].detach().requires_grad_()
+            q = d["quat"].detach().requires_grad_()
+            with dpc.options(voxels=False, drc_probs=False):     # the default path is reproducible
+                out = dpc.pointcloud_project_fast(cfg, pts, q, None, None, kern)
+            (gp,) = torch.autograd.grad((out["proj"] * w).sum(), [pts])
+            pipe.download({"mask": out["proj"], "g_points": gp}, host[lane][k])
+        return step
+
+    def eager():
+        res = []
+        for lane in range(L):
+            pipe = dpc.HostPipeline(dev)
+            step = make_step(lane, pipe)
+            for k in range(S):
+                step(k)
+            pipe.drain()
+            res.append([{n: t.clone() for n, t in h.items()} for h in host[lane]])
+        return res
+
+    ref = eager()
+    ag = dpc.AlternatingGraphs(make_step, S, dev, lanes=L)
+    for rep in range(2):
+        for lane in range(L):
+            for h in host[lane]:
+                for t in h.values():
+                    t.zero_()
+        for _ in range(L):
+            ag.replay()
+        ag.join()
+        torch.cuda.synchronize()
+        for lane in range(L):
+            for r, h in zip(ref[lane], host[lane]):
+                for n in r:
+                    assert torch.equal(r[n], h[n]), (rep, lane, n)
