@@ -71,11 +71,11 @@ def stage_algorithmic_bytes(N, V, Vz):
 # DRAM bytes per whole-batch launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's
 # kernel(s) at workload A, from the committed `ncu --set full` capture NCU_CAPTURE (cold L2: ncu
 # flushes the caches before every replay).  None = not captured for that workload.
-NCU_CAPTURE = "profiles/r01_ncu_full_step_fast_ray_state.csv"
+NCU_CAPTURE = "profiles/r01_ncu_full_step_final.csv"
 NCU_TRAFFIC_BYTES = {
-    "A": {"pose_scatter": 6.16e6 + 8.72e6, "blur_xy_fwd": 7.46e6 + 12.18e6,
-          "blurz_drc_fwd": 67.16e6 + 14.18e6, "drc_blurz_bwd": 71.37e6 + 24.96e6,
-          "blur_xy_bwd": 77.22e6 + 4.59e6, "gather_pose_bwd": 23.12e6 + 0.0},
+    "A": {"pose_scatter": 6.17e6 + 8.72e6, "blur_xy_fwd": 7.47e6 + 11.73e6,
+          "blurz_drc_fwd": 67.15e6 + 13.35e6, "drc_blurz_bwd": 71.35e6 + 22.70e6,
+          "blur_xy_bwd": 76.99e6 + 5.79e6, "gather_pose_bwd": 23.12e6 + 0.0},
 }
 
 
@@ -377,7 +377,9 @@ def run_b200(args, rank, world, local_rank):
             # host (~0.25 ms of Python / autograd-engine work per ~0.15 ms step); two lanes
             # replayed in turn keep the copy pipeline from draining at every replay boundary
             ag = dpc.AlternatingGraphs(make_step, E2E_GRAPH_STEPS, dev, lanes=E2E_LANES, warmup=2)
-            reps = (args.steps + E2E_GRAPH_STEPS - 1) // E2E_GRAPH_STEPS
+            # at least 8 replays (the first replay of every lane ramps its copy pipeline up), a
+            # multiple of the lane count; the time is scaled to args.steps below
+            reps = max(8, (args.steps + E2E_GRAPH_STEPS - 1) // E2E_GRAPH_STEPS)
             reps += reps % E2E_LANES and (E2E_LANES - reps % E2E_LANES)
 
             def replay_e2e(i):
