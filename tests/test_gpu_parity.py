@@ -91,6 +91,32 @@ def test_golden_forward_and_gradients(dpc, name):
         assert _golden.rel_err(g, rec["grad_" + k].reshape(g.shape)) < GRAD_TOL, k
 
 
+@pytest.mark.parametrize("V,K,sigma,N,P,scaled", [
+    (32, 11, 1.5, 1, 1, True), (32, 3, 0.4, 37, 3, True), (32, None, None, 500, 2, False),
+    (64, 5, 0.6, 1000, 3, True), (64, 21, 3.0, 4000, 2, False), (64, 11, 2.0, 333, 1, True),
+    (128, 21, 3.0, 3000, 1, True), (128, 7, 1.0, 100, 2, False)])
+def test_fast_ray_state_matches_general_layout(dpc, V, K, sigma, N, P, scaled):
+    """Without the optional outputs the ray kernels keep the signed clipped occupancy and
+    transmittance checkpoints and run the one-sweep bulk-copy backward; with them they keep B and
+    run the two-sweep one.  Same mathematics: every output and gradient agrees to rounding, over
+    tap radii (0, 1, 2, 5, 10 -> every ring length), grid sizes, tiny and ragged clouds."""
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=K or 11)
+    case = _inputs.make_case(cfg, P, N, 31 * V + N, translation=True, focal=True, scale=scaled,
+                             screened=False)
+    case["kernel"] = None if K is None else CF.smoothing_taps(cfg, sigma)
+    out_g, loss_g, grads_g = run_cuda(dpc, cfg, case, P, V)
+    dpc.set_outputs(voxels=False, drc_probs=False)
+    try:
+        out_f, loss_f, grads_f = run_cuda(dpc, cfg, case, P, V)
+    finally:
+        dpc.set_outputs(voxels=True, drc_probs=True)
+    for k in ("proj", "proj_depth"):
+        assert _golden.rel_err(out_f[k], out_g[k]) < 1e-6, k
+    assert torch.equal(out_f["tr_pc"], out_g["tr_pc"])
+    for k in grads_g:
+        assert _golden.rel_err(grads_f[k], grads_g[k]) < 2e-5, k
+
+
 @pytest.mark.parametrize("kind", ["uniform", "clustered"])
 def test_default_path_is_reproducible(dpc, kind):
     """The plane scatter accumulates in biased fixed point with integer atomics (order-free) and
