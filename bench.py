@@ -500,7 +500,14 @@ def run_b200(args, rank, world, local_rank):
                              "half-batch launches of every kernel on two streams" % n_chunks,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": sbytes[top] * P,
-                     "kernel_ms": stages[top]},
+                     "kernel_ms": stages[top],
+                     # the same kernel against the bytes it really moves (ncu) -- far below the
+                     # HBM peak: its ceilings are shared-memory bandwidth and FP32 FMA issue
+                     # (timing probes)
+                     "traffic_gbs": (None if (args.global_grid or NCU_TRAFFIC_BYTES.get(
+                         args.workload, {}).get(top) is None) else
+                         NCU_TRAFFIC_BYTES[args.workload][top] / (stages[top] * 1e-3) / 1e9),
+                     "limiter": "shared-memory bandwidth / FP32 FMA issue, not HBM"},
         "roofline_step": {"algorithmic_bytes_per_projection": algorithmic_bytes(N, V, Vz),
                           "frac": step_frac, "peak": peak, "unit": "GB/s"},
         "stage_ms": stages,
