@@ -103,13 +103,16 @@ struct XYCfg {
 // IN: how a window element becomes the value to blur: 0 as stored; 1 clamp(raw, 0, 1) of a
 // non-negative raw value = min(v, 1); 2 the plane scatter's biased fixed point (see
 // scatter_add_fixed): the tile holds 1 + raw, so clamp(raw, 0, 1) = min(v, 2) - 1, exactly
-template <int R, int J, int W2, int IN = 0>
+// SKIP_LO / SKIP_HI: the first / last so many window positions are known to be zero padding (the
+// block at the start / end of a line): their loads and their FFMA2 are left out.
+template <int R, int J, int W2, int IN = 0, int SKIP_LO = 0, int SKIP_HI = 0>
 __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, const u64 (&k2)[2 * R + 1],
                                             u64 (&acc)[J]) {
 #pragma unroll
   for (int j = 0; j < J; ++j) acc[j] = 0;
 #pragma unroll
   for (int i = 0; i < W2; ++i) {
+    if (2 * i + 1 < SKIP_LO || 2 * i >= 2 * W2 - SKIP_HI) continue;   // a pair of pad positions
     float4 v4 = *reinterpret_cast<const float4 *>(win + 2 * i);
     if (IN == 1) {
       v4.x = fminf(v4.x, 1.f);
@@ -136,6 +139,27 @@ __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, cons
       }
     }
   }
+}
+
+// Edge-aware window pass: the first and the last block of a line see R pad positions on one side
+// (8 % of the FFMA2, 14 % of those warps' LDS.128).  The block index is warp-uniform, so the three
+// variants do not diverge -- but they are three copies of the unrolled pass: at 64^2, where two of
+// a CTA's four warps are edge warps, the instruction-cache misses cost more than the skipped work
+// (38.0 -> 42.7 us forward, 43.2 -> 47.2 us backward); at 128^2 (two of eight blocks) it pays
+// (532 -> 529 us, 488 -> 473 us).  EDGES is therefore set for V >= 128 only.
+#ifndef DPC_XY_EDGES
+#define DPC_XY_EDGES 1
+#endif
+template <int R, int J, int W2, int IN, bool EDGES>
+__device__ __forceinline__ void window_pass(const float2 *__restrict__ win, const u64 (&k2)[2 * R + 1],
+                                            u64 (&acc)[J], int block, int nblocks) {
+  constexpr int PADS = R & ~1;   // whole pairs only
+  if (EDGES && DPC_XY_EDGES && nblocks > 1 && block == 0)
+    window_fma2<R, J, W2, IN, PADS, 0>(win, k2, acc);
+  else if (EDGES && DPC_XY_EDGES && nblocks > 1 && block == nblocks - 1)
+    window_fma2<R, J, W2, IN, 0, PADS>(win, k2, acc);
+  else
+    window_fma2<R, J, W2, IN, 0, 0>(win, k2, acc);
 }
 
 __device__ __forceinline__ float4 clamp01(float4 v) {
@@ -360,8 +384,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     for (int task = tid; task < C::XTASKS; task += C::THREADS) {
       const int rp = task % HALF, x0 = (task / HALF) * C::J;
       u64 acc[C::J];
-      window_fma2<R, C::J, C::W2, FIXED ? 2 : (POINTS && WRITE_BITS ? 1 : 0)>(A2 + rp * C::S + x0,
-                                                                               k2, acc);
+      window_pass<R, C::J, C::W2, FIXED ? 2 : (POINTS && WRITE_BITS ? 1 : 0), V >= 128>(
+          A2 + rp * C::S + x0, k2, acc, task / HALF, V / C::J);
       if (C::ONE_TILE) __syncthreads();   // every window is in registers: the tile can be reused
       if (FIXED) {                        // the pads held the bias: zero padding for the Y pass
         constexpr int PADP = C::S - V;
@@ -454,7 +478,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   for (int task = tid; task < C::YTASKS; task += C::THREADS) {
     const int cp = task % (V / 2), y0 = (task / (V / 2)) * C::J;
     u64 acc[C::J];
-    window_fma2<R, C::J, C::W2>(B2 + cp * C::S + y0, k2, acc);
+    window_pass<R, C::J, C::W2, 0, V >= 128>(B2 + cp * C::S + y0, k2, acc,
+                                                       task / (V / 2), V / C::J);
     if (GATHER && G_OVER_TILE) __syncthreads();   // every window is in registers
 #pragma unroll
     for (int j = 0; j < C::J; ++j) {
