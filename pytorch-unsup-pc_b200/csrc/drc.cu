@@ -169,6 +169,9 @@ __device__ __forceinline__ u64 ring_dot2(const u64 (&ring)[L], const u64 (&k2)[2
     const u64 v = ring[(first + t) % L];
     const u64 k = reversed ? k2[W - 1 - t] : k2[t];
     // the first term of every chain is a plain product: no zeroed accumulator registers
+#ifdef DPC_PROBE_FEW_TAPS
+    if (t >= 2 * NACC) continue;      // timing probe: 2 * NACC taps of 2R+1
+#endif
     acc[t % NACC] = t < NACC ? mul2(k, v) : fma2(k, v, acc[t % NACC]);
   }
 #pragma unroll
@@ -621,8 +624,13 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
         gB2 = mul2(gv2, s2);
       }
       ring[j] = gB2;
-      if (store_all || k + R < VZ)
+      if (store_all || k + R < VZ) {
+#ifdef DPC_PROBE_NO_STORE
+        ds2 = add2(ds2, ring_dot2<R, L>(ring, k2, j, true));     // timing probe: no g_grid store
+#else
         *reinterpret_cast<u64 *>(gout + (size_t)j * VV) = ring_dot2<R, L>(ring, k2, j, true);
+#endif
+      }
     }
   };
 #pragma unroll
