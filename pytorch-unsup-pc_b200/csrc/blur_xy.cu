@@ -340,9 +340,11 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       // clamp(raw, 0, 1) happens in the X pass, on the window loads
     }
     // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
-#ifdef DPC_XY_UNROLL_FILL
-#pragma unroll
+#ifndef DPC_XY_UNROLL_FILL
+#define DPC_XY_UNROLL_FILL 1
 #endif
+    constexpr int kFillUnroll = DPC_XY_UNROLL_FILL;
+#pragma unroll kFillUnroll
     for (int i = tid; i < ((POINTS && WRITE_BITS) ? 0 : C::FILL_ITEMS); i += C::THREADS) {
       const int rp = i / (V / 4), c4 = i % (V / 4);
       const int r0 = h * C::RH + rp, r1 = r0 + HALF;
