@@ -41,6 +41,38 @@
 
 namespace dpc {
 
+// ---- A/B switches (scripts/build_variant.sh <name> -D<switch>=<value>) -------------------------
+// Every default below is the measured winner; DESIGN.md section 5 lists the numbers.
+#ifndef DPC_XY_J
+#define DPC_XY_J 16            // outputs per line per thread (8: more window reads; 32: too few threads)
+#endif
+#ifndef DPC_XY_RH128
+#define DPC_XY_RH128 128       // plane rows per X-pass round at V = 128 (64: two tiles, 1 CTA per SM)
+#endif
+#ifndef DPC_XY_MINB64
+#define DPC_XY_MINB64 9        // resident CTAs per SM the 64^2 kernels' registers are sized for
+#endif
+#ifndef DPC_XY_SPARSE_Q
+#define DPC_XY_SPARSE_Q 3      // sparse last adjoint pass up to Q/4 touching points per thread (0: never)
+#endif
+#ifndef DPC_XY_EDGES
+#define DPC_XY_EDGES 1         // edge blocks skip their padding (applied for V >= 128 only)
+#endif
+#ifndef DPC_XY_PREFETCH
+#define DPC_XY_PREFETCH 1      // touching-point range + first record loaded at kernel entry
+#endif
+#ifndef DPC_XY_PADZERO
+#define DPC_XY_PADZERO 1       // zero only the pads when the fill overwrites the interior (V >= 128)
+#endif
+#ifndef DPC_XY_FIXED
+#define DPC_XY_FIXED 1         // biased fixed-point plane scatter (0: fp32 compare-and-swap adds)
+#endif
+#ifndef DPC_XY_UNROLL_FILL
+#define DPC_XY_UNROLL_FILL 1   // unroll factor of the tile fill
+#endif
+// DPC_PROBE_FEW_FMA / _NO_SCATTER / _NO_FILL / _NO_MASK / _NO_GATHER: timing probes that leave one
+// phase out (WRONG results; used once to find out what the kernels' time is made of).
+
 typedef unsigned long long u64;
 
 __device__ __forceinline__ u64 bx_pack2(float lo, float hi) {
@@ -61,21 +93,12 @@ __device__ __forceinline__ u64 bx_fma2(u64 a, u64 b, u64 c) {
 // the last adjoint pass at the points only (0 = always the dense pass; A/B switch).  The sparse
 // pass trades 336 FFMA2 per thread for ~33 randomly addressed LDS.64 per point: measured faster at
 // 0.4 points per thread (workload B: 600 -> 489 us), slower at 1.6 (workload A: 44 -> 53 us).
-#ifndef DPC_XY_SPARSE_Q
-#define DPC_XY_SPARSE_Q 3
-#endif
 
 template <int V, int R>
 struct XYCfg {
-#ifndef DPC_XY_J
-#define DPC_XY_J 16
-#endif
   static constexpr int J = DPC_XY_J;                 // outputs per line per thread
   static constexpr int W = J + 2 * R;                // window positions (even)
   static constexpr int W2 = W / 2;                   // LDS.128 per window
-#ifndef DPC_XY_RH128
-#define DPC_XY_RH128 128
-#endif
   // plane rows staged per X-pass round: the whole plane (one tile, reused for the transposed
   // layout).  DPC_XY_RH128=64: two rounds of 64 rows at V = 128 (two tiles, 115 KB, 1 CTA/SM)
   static constexpr int RH = V <= 64 ? V : DPC_XY_RH128;
@@ -90,9 +113,6 @@ struct XYCfg {
   static constexpr bool ONE_TILE = (RH == V);
   static constexpr int TILE_LINES = ONE_TILE ? V / 2 : RH / 2 + V / 2;
   static constexpr size_t SMEM = (size_t)TILE_LINES * S * sizeof(float2);
-#ifndef DPC_XY_MINB64
-#define DPC_XY_MINB64 9
-#endif
   static constexpr int MINB = V == 64 ? DPC_XY_MINB64 : (V == 128 && RH == V ? 2 : 1);
   static_assert(V % 32 == 0, "V must be a multiple of 32");
   static_assert(FILL_ITEMS % THREADS == 0, "fill loop must be warp-uniform");
@@ -147,9 +167,6 @@ __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, cons
 // a CTA's four warps are edge warps, the instruction-cache misses cost more than the skipped work
 // (38.0 -> 42.7 us forward, 43.2 -> 47.2 us backward); at 128^2 (two of eight blocks) it pays
 // (532 -> 529 us, 488 -> 473 us).  EDGES is therefore set for V >= 128 only.
-#ifndef DPC_XY_EDGES
-#define DPC_XY_EDGES 1
-#endif
 template <int R, int J, int W2, int IN, bool EDGES>
 __device__ __forceinline__ void window_pass(const float2 *__restrict__ win, const u64 (&k2)[2 * R + 1],
                                             u64 (&acc)[J], int block, int nblocks) {
@@ -258,21 +275,12 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   const int pb = POINTS ? (int)(plane / Vz) : 0, pz = POINTS ? (int)(plane - (size_t)pb * Vz) : 0;
   TouchRange touch = {0u, 0u, 0u, nullptr};
   uint4 rec0 = make_uint4(0u, 0u, 0u, 0u);
-#ifndef DPC_XY_PREFETCH
-#define DPC_XY_PREFETCH 1
-#endif
-#ifndef DPC_XY_PADZERO
-#define DPC_XY_PADZERO 1
-#endif
   if (POINTS && DPC_XY_PREFETCH) {
     touch = touch_range(cells, pb, pz, N);
     rec0 = first_touching_record(touch, tid);
   }
   // (pads only: measured 498 -> 484 us at 128^2, but 43.0 -> 46.7 us at 64^2, where the whole
   // tile is 11 vector stores per thread)
-#ifndef DPC_XY_FIXED
-#define DPC_XY_FIXED 1
-#endif
   // fixed-point plane scatter (one-tile layouts): the tile starts as the bias 1.0f, pads included,
   // so that the X pass decodes every window element alike; the pads are zeroed for the Y pass
   constexpr bool FIXED = POINTS && WRITE_BITS && C::ONE_TILE && DPC_XY_FIXED;
@@ -340,9 +348,6 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       // clamp(raw, 0, 1) happens in the X pass, on the window loads
     }
     // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
-#ifndef DPC_XY_UNROLL_FILL
-#define DPC_XY_UNROLL_FILL 1
-#endif
     constexpr int kFillUnroll = DPC_XY_UNROLL_FILL;
 #pragma unroll kFillUnroll
     for (int i = tid; i < ((POINTS && WRITE_BITS) ? 0 : C::FILL_ITEMS); i += C::THREADS) {

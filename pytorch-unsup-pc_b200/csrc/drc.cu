@@ -48,27 +48,31 @@
 
 namespace dpc {
 
-// A/B switches (scripts/build_variant.sh): compile-time depth specialisation of the forward /
-// backward ray kernels, resident CTAs per SM the backward's register budget is sized for
+// ---- A/B switches (scripts/build_variant.sh <name> -D<switch>=<value>) -------------------------
+// Every default is the measured winner; DESIGN.md section 5 lists the numbers.
 #ifndef DPC_VZ_FWD
-#define DPC_VZ_FWD 1
+#define DPC_VZ_FWD 1           // compile-time depth in the forward ray kernel (0: run-time range checks)
 #endif
 #ifndef DPC_VZ_BWD
-#define DPC_VZ_BWD 1
-#endif
-#ifndef DPC_BWD_MINB
-#define DPC_BWD_MINB 4
+#define DPC_VZ_BWD 1           // ... and in the general-layout backward
 #endif
 #ifndef DPC_FWD_MINB
-#define DPC_FWD_MINB 1
+#define DPC_FWD_MINB 1         // resident CTAs per SM the forward's registers are sized for (1: no cap)
+#endif
+#ifndef DPC_BWD_MINB
+#define DPC_BWD_MINB 4         // ... and the backward's (4: 252 registers; 6: 168; 8: 128 + spills)
 #endif
 #ifndef DPC_FWD_L10
-#define DPC_FWD_L10 28
+#define DPC_FWD_L10 28         // ring / ray-block length at tap radius 10 (24, 28, 32 measured)
 #endif
-constexpr int kFwdThreads = 128;   // ray pairs per CTA (forward)
 #ifndef DPC_BWD_THREADS
-#define DPC_BWD_THREADS 64
+#define DPC_BWD_THREADS 64     // ray pairs per backward CTA (32, 64, 128: no difference)
 #endif
+#ifndef DPC_RING_NACC
+#define DPC_RING_NACC 2        // independent accumulation chains of the ring dot product
+#endif
+// DPC_PROBE_FEW_TAPS / DPC_PROBE_NO_STORE: timing probes (WRONG results).
+constexpr int kFwdThreads = 128;                // ray pairs per CTA (forward)
 constexpr int kBwdThreads = DPC_BWD_THREADS;    // ray pairs per CTA (backward)
 
 int drc_scale_partial_blocks(int V) { return V * V / (2 * kBwdThreads); }
@@ -153,9 +157,6 @@ static RayConst make_ray_const(const DrcArgs &a) {
   return c;
 }
 
-#ifndef DPC_RING_NACC
-#define DPC_RING_NACC 2
-#endif
 // sum_t k[t] * ring[(first + t) % L]  (reversed: k[2R - t]), packed pairs
 template <int R, int L>
 __device__ __forceinline__ u64 ring_dot2(const u64 (&ring)[L], const u64 (&k2)[2 * R + 1],
