@@ -138,7 +138,10 @@ pose_cells_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
 // projection.  The order inside a cell is arbitrary (the consumers accumulate
 // with atomics or write per-point results); the cell boundaries are exact.
 constexpr int kBinThreads = 256;
-constexpr int kBinSplit = 4;
+#ifndef DPC_BIN_SPLIT
+#define DPC_BIN_SPLIT 4
+#endif
+constexpr int kBinSplit = DPC_BIN_SPLIT;      // CTAs per projection (one cluster)
 constexpr int kMaxBins = 192;
 __global__ void __cluster_dims__(kBinSplit, 1, 1) __launch_bounds__(kBinThreads)
 bin_points_kernel(CellsView cells, int N, int Vz) {
