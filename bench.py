@@ -48,6 +48,10 @@ WORKLOADS = {
     "B": dict(name="paper scale: batch 32 x 4 candidates, 16000 pts -> 128^3 -> 128^2, K=21 "
                    "sigma=3.0, fwd+bwd",
               P=128, N=16000, V=128, K=21, sigma=3.0),
+    # BASELINE.json configs[2], the projection part per GPU: batch 16 x 4 views x 4 candidates
+    "C3": dict(name="chair_unsupervised train-step shapes per GPU: batch 16 x 4 views x 4 candidates, "
+                    "8000 pts -> 64^3 -> 64^2, K=21 sigma=3.0, fwd+bwd",
+               P=256, N=8000, V=64, K=21, sigma=3.0),
 }
 N_INPUT_SETS = 3          # distinct input sets rotated between steps
 E2E_GRAPH_STEPS = int(os.environ.get("DPC_E2E_GRAPH_STEPS", "24"))   # e2e steps captured per CUDA graph (a multiple of N_INPUT_SETS)
@@ -492,7 +496,7 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        P_cpu = 8 if args.workload == "A" else 1
+        P_cpu = 1 if args.workload == "B" else 8
         v, times = cpu_reference_rate(w, P_cpu, reps=3, warm=1, threads=threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d projections of the same workload, fwd+bwd, 1 warm-up + median of 3 "
