@@ -15,13 +15,14 @@ _ws_cache = {}
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    # a plain int converts to void* as well as a c_void_p object does, and costs no allocation
+    return None if t is None else t.data_ptr()
 
 
 def _stream(device):
     # the raw handle of torch's current stream (torch.cuda.current_stream() builds a
     # Python Stream object every call: ~10 us, which matters at ~200 us per step)
-    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(device.index))
+    return torch._C._cuda_getCurrentRawStream(device.index)
 
 
 class _on_device:
@@ -100,14 +101,27 @@ def _tap_args(taps):
         return (None, 0, None, 0, None, 0)
     args = []
     for k in taps:
-        args += [ctypes.c_void_p(k.data_ptr()), int(k.numel())]
+        args += [k.data_ptr(), int(k.numel())]
     return tuple(args)
+
+
+_size_cache = {}
+
+
+def _sizes(params):
+    """(workspace bytes, saved cell-record bytes) of a geometry, asked from the library once."""
+    key = (params.P, params.N, params.Vz, params.V)
+    v = _size_cache.get(key)
+    if v is None:
+        lib = _lib.load()
+        v = (lib.dpc_workspace_bytes(ctypes.byref(params)), lib.dpc_cells_bytes(ctypes.byref(params)))
+        _size_cache[key] = v
+    return v
 
 
 def _workspace(params, device):
     """One cached workspace per (device, size class); stream-ordered reuse."""
-    need = _lib.load().dpc_workspace_bytes(ctypes.byref(params))
-    return _scratch("ws", need, device)
+    return _scratch("ws", _sizes(params)[0], device)
 
 
 def _scratch(kind, nbytes, device):
@@ -153,11 +167,11 @@ class ProjectFn(torch.autograd.Function):
         use_cells = int(mode) == _lib.SCATTER_ATOMIC and plane_local
         n_grid = P * Vz * V * V * 4
         n_bits = P * Vz * V * (V // 32) * 4
-        n_cells = lib.dpc_cells_bytes(ctypes.byref(params)) if use_cells else 0
+        n_cells = _sizes(params)[1] if use_cells else 0
         state = torch.empty(n_grid + n_bits + n_cells, dtype=torch.uint8, device=dev)
         base = state.data_ptr()
-        grid_b, bits = ctypes.c_void_p(base), ctypes.c_void_p(base + n_grid)
-        cells = ctypes.c_void_p(base + n_grid + n_bits) if use_cells else None
+        grid_b, bits = base, base + n_grid
+        cells = base + n_grid + n_bits if use_cells else None
         ws = _workspace(params, dev)
         tail = (_ptr(points), _ptr(quat), _ptr(trans), _ptr(focal),
                 _ptr(scale), *_tap_args(taps), int(mode), _ptr(tr_pc), grid_b, bits,
@@ -184,8 +198,8 @@ class ProjectFn(torch.autograd.Function):
         points, quat, trans, focal, scale, state, sel = ctx.saved_tensors
         n_grid, n_bits, use_cells = ctx.state_layout
         base = state.data_ptr()
-        grid_b, bits = ctypes.c_void_p(base), ctypes.c_void_p(base + n_grid)
-        cells = ctypes.c_void_p(base + n_grid + n_bits) if use_cells else None
+        grid_b, bits = base, base + n_grid
+        cells = base + n_grid + n_bits if use_cells else None
         params = ctx.params
         dev = points.device
         P, N, Vz, V = params.P, params.N, params.Vz, params.V
