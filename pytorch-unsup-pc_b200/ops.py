@@ -238,6 +238,28 @@ class ProjectFn(torch.autograd.Function):
         return (g_points, g_quat, g_trans, g_focal, g_scale) + (None,) * 7
 
 
+def project(points, quat, trans, focal, scale, params, taps, want_voxels, want_probs, mode,
+            plane_local=True, rep=None):
+    """The whole-path op: through the C++ autograd binding when lib/dpc_b200_torch.so is built
+    (no Python in either pass), else through ``ProjectFn`` (ctypes).  Same C ABI, same kernels,
+    same results.  Returns (mask, depth, tr_pc, voxels or None, probs or None)."""
+    from . import _torch_binding
+    ext = _torch_binding.load()
+    if ext is None:
+        return ProjectFn.apply(points, quat, trans, focal, scale, params, taps, want_voxels,
+                               want_probs, mode, plane_local, rep)
+    geom = [params.P, params.N, params.Vz, params.V, params.camera_distance, params.focal_length,
+            params.max_depth, params.drc_clip, params.drc_logsum, params.flip_y]
+    kx, ky, kz = taps if taps is not None else (None, None, None)
+    replicas, n_src, sel = (0, 0, None) if rep is None else (int(rep[0]), int(rep[1]), rep[2])
+    out = ext.project(points, quat, trans, focal, scale, geom, kx, ky, kz, bool(want_voxels),
+                      bool(want_probs), int(mode), bool(plane_local), replicas, n_src, sel)
+    mask, depth, tr_pc = out[:3]
+    voxels = out[3] if want_voxels else None
+    probs = out[3 + bool(want_voxels)] if want_probs else None
+    return mask, depth, tr_pc, voxels, probs
+
+
 class PoseFn(torch.autograd.Function):
     """pc_perspective_transform (point_cloud_to.py:118-178, quaternion branch)."""
 

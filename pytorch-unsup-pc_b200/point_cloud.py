@@ -232,7 +232,7 @@ def pointcloud_project_replicated(cfg, point_cloud, transform, predicted_transla
     col = None if all_rgb is None else _features(all_rgb, pts)      # [B,N,C], un-replicated too
     params = ops.make_params(cfg, P, N, flip_y=True)
     taps = ops.host_taps(kernel)
-    mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
+    mask, depth, tr_pc, voxels, probs = ops.project(
         pts, quat, trans, focal, scale, params, taps,
         _options["voxels"], _options["drc_probs"] or col is not None, _scatter_mode(),
         _options["plane_local"], (P // B, N_src, sel))
@@ -281,7 +281,7 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation, 
     params = ops.make_params(cfg, P, N, flip_y=True)
     taps = ops.host_taps(kernel)
     # the colour integral needs the ray-event probabilities, asked for or not
-    mask, depth, tr_pc, voxels, probs = ops.ProjectFn.apply(
+    mask, depth, tr_pc, voxels, probs = ops.project(
         pts, quat, trans, focal, scale, params, taps,
         _options["voxels"], _options["drc_probs"] or col is not None, _scatter_mode(),
         _options["plane_local"])
