@@ -2,7 +2,7 @@
 """Minimal fwd+bwd loop of the projection through the C ABI (device-resident
 inputs, no CUDA graph) -- the command ncu wraps (B200_PROFILING.md):
 
-    python scripts/profile_step.py [--workload A|B] [--steps 3] [--global-grid]
+    python scripts/profile_step.py [--workload A|B] [--steps 3] [--global-grid] [--P n] [--N n]
 
 Each step launches, in order: pose_cells, blur_xy (plane scatter), blurz_drc_fwd,
 drc_blurz_bwd, blur_xy (plane gather), gather_pose_bwd  -> 6 kernels per step.
@@ -25,9 +25,15 @@ def main():
     ap.add_argument("--workload", default="A")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--global-grid", action="store_true", help="memset + global scatter path")
+    ap.add_argument("--P", type=int, default=0, help="override the workload's projection count")
+    ap.add_argument("--N", type=int, default=0, help="override the workload's point count")
     a = ap.parse_args()
     lib = _lib.load()
-    w = bench.WORKLOADS[a.workload]
+    w = dict(bench.WORKLOADS[a.workload])
+    if a.P:
+        w["P"] = a.P
+    if a.N:
+        w["N"] = a.N
     cfg = bench.make_cfg(w)
     dev = torch.device("cuda:0")
     P, N, V = w["P"], w["N"], w["V"]

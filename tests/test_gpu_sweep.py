@@ -1,0 +1,70 @@
+"""GPU parity sweep: seeded random draws over the whole argument space of the path
+(grid size, anisotropic depth, tap count and sigma, ragged cloud sizes, batch sizes on both sides
+of the half-batch threshold, optional pose inputs, DRC form, optional outputs, scatter mode)
+against the CPU oracle (oracle/closed_form.py, pinned to the reference by
+tests/test_oracle_pinning.py).
+
+Tolerances as in tests/test_gpu_parity.py (BASELINE.json north_star): forward 1e-5, gradients
+1e-4, relative to the tensor's max; gradient cases use boundary-screened inputs.
+"""
+import random
+
+import pytest
+import torch
+
+import _golden
+import _inputs
+from oracle import closed_form as CF
+from oracle.config import default_cfg
+from test_gpu_parity import FWD_TOL, GRAD_TOL, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def draw(i):
+    """Draw number i: a dict of settings, a pure function of i."""
+    r = random.Random(9000 + i)
+    V = r.choice([32, 32, 64])
+    vz = r.choice([-1, -1, 16, 24, 48] if V == 32 else [-1, -1, 32, 40])
+    K = r.choice([1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21])
+    if vz > V:
+        K = min(K, 13)          # the depth taps scale with vox_size_z / vox_size (<= 21 taps)
+    heavy = V == 64
+    P = r.choice([1, 2, 3, 5] if heavy else [1, 2, 3, 7, 64, 65, 66])
+    N = r.choice([1, 2, 31, 32, 33, 257, 1000, 2049] + ([] if P > 8 else [4097, 8000]))
+    return dict(V=V, vz=vz, K=K, sigma=r.uniform(0.2, 3.0), P=P, N=N,
+                kind=r.choice(["uniform", "clustered"]), translation=r.random() < 0.5,
+                focal=r.random() < 0.5, scale=r.random() < 0.7, logsum=r.random() < 0.8,
+                outputs=r.random() < 0.5, deterministic=r.random() < 0.3,
+                no_blur=r.random() < 0.1)
+
+
+@pytest.fixture(scope="module")
+def dpc():
+    import pytorch_unsup_pc_b200 as m
+    m._lib.load()
+    return m
+
+
+@pytest.mark.parametrize("i", range(24))
+def test_random_draw_matches_oracle(dpc, i):
+    d = draw(i)
+    cfg = default_cfg(vox_size=d["V"], vox_size_z=d["vz"], pc_gauss_kernel_size=d["K"],
+                      drc_logsum=d["logsum"])
+    case = _inputs.make_case(cfg, d["P"], d["N"], 7000 + i, kind=d["kind"],
+                             translation=d["translation"], focal=d["focal"], scale=d["scale"],
+                             screened=True)
+    case["kernel"] = None if d["no_blur"] else CF.smoothing_taps(cfg, d["sigma"])
+    o_out, o_loss, o_grads = run_oracle(cfg, case, d["P"], d["V"])
+    with dpc.options(deterministic=d["deterministic"], voxels=d["outputs"],
+                     drc_probs=d["outputs"]):
+        c_out, c_loss, c_grads = run_cuda(dpc, cfg, case, d["P"], d["V"])
+    keys = ("proj", "proj_depth", "tr_pc") + (("voxels", "drc_probs") if d["outputs"] else ())
+    errs = {k: _golden.rel_err(c_out[k], o_out[k]) for k in keys}
+    gerrs = {k: _golden.rel_err(c_grads[k], o_grads[k]) for k in o_grads
+             if float(o_grads[k].abs().max()) > 0}
+    print(i, d, {k: "%.1e" % v for k, v in errs.items()}, {k: "%.1e" % v for k, v in gerrs.items()})
+    for k, v in errs.items():
+        assert v < FWD_TOL, (d, k, v)
+    for k, v in gerrs.items():
+        assert v < GRAD_TOL, (d, k, v)
