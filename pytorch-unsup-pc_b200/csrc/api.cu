@@ -31,6 +31,14 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Profiling hook (dpc_project_profile): when set, an event is recorded after
 // every stage of dpc_project_fwd / dpc_project_bwd on the launching stream.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("DPC_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 static thread_local cudaEvent_t *tl_stage_events = nullptr;
 static thread_local int tl_stage_idx = 0;
 static inline void stage_mark(cudaStream_t s) {

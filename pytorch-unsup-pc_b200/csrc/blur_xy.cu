@@ -269,6 +269,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   const int tid = threadIdx.x;
   const size_t plane = blockIdx.x;
   const float *sp = src + plane * V * V;
+  pdl_wait();             // sorted records (forward) / the gradient grid (backward)
+  pdl_release();
 
   // the points touching this plane: the range now, the thread's first record right behind it --
   // both are in flight while the tile is zeroed (forward) / filled and blurred (backward)
@@ -543,9 +545,8 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
       cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT>,                               \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     }                                                                                          \
-    blur_xy_kernel<V, R, CL, WB, MO, PT><<<g, t, smem, s>>>(a.src, a.dst, a.bits_out,          \
-                                                            a.bits_in, KX, KY, a.cells, a.part, \
-                                                            a.Vz, a.N, a.P);                   \
+    launch_dep(blur_xy_kernel<V, R, CL, WB, MO, PT>, g, t, smem, s, a.src, a.dst, a.bits_out,  \
+               a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P);                            \
   } while (0)
   const bool points = a.cells.cellz != nullptr;
   if (points && (a.Vz < 1 || a.N < 1 || a.P < 1 || (!a.bits_in && !a.bits_out) ||

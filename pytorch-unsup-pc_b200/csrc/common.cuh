@@ -60,6 +60,50 @@ struct DeviceOnce {
   }
 };
 
+// ---- programmatic dependent launch ------------------------------------------
+// The hot chain (pose_cells -> bin_points -> blur_xy -> blurz_drc_fwd; drc_blurz_bwd ->
+// blur_xy -> gather_pose_bwd) runs as stream-ordered kernels of a few tens of microseconds.
+// Launched with `launch_dep` (cudaLaunchAttributeProgrammaticStreamSerialization; inside a
+// captured graph: a programmatic edge), kernel k+1 is set up while kernel k still runs and
+// blocks in `pdl_wait()` (griddepcontrol.wait: returns when kernel k has completed and its
+// writes are visible), so its launch latency leaves the critical path.
+// RULES: a kernel launched with `launch_dep` calls `pdl_wait()` on every path before its first
+// global-memory access (read OR write), and `pdl_release()` only after its own wait, so at most
+// one dependent kernel is resident early.  Without the launch attribute both are no-ops.
+// Measured at workload A (B200, graph replay): no attribute 146.2 us per step, e2e 307.5 k
+// proj/s; attribute + explicit early release at kernel entry (DPC_PDL_EARLY=1:
+// griddepcontrol.launch_dependents, the dependent's CTAs become resident as this kernel's last
+// wave drains) 143.0 us but e2e 303.3 k -- the waiting CTAs hold slots that the other lane's
+// kernels would have used; attribute without explicit release (the default: the dependent
+// launches as this kernel's last CTAs exit) 143.4 us, e2e 309.2 k.
+// DPC_PDL=0 (env) launches the same kernels without the attribute (A/B).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef DPC_PDL_EARLY
+#define DPC_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void pdl_release() {
+  if (DPC_PDL_EARLY) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args &&>(args)...);
+}
+
 // ---- kernel launchers (defined in the .cu files) ---------------------------
 struct PoseArgs {
   const float *points, *quat, *trans, *focal;

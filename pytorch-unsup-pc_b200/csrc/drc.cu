@@ -273,6 +273,8 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   int b, yx, oi;
   pair_index<V>(c, kFwdThreads, b, yx, oi);
   const size_t col0 = (size_t)b * c.Vz * VV + yx;
+  pdl_wait();             // the XY-blurred grid comes from blur_xy
+  pdl_release();
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
   const u64 s2 = pack2(s, s), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
   const u64 ec2 = pack2(c.exp_clip, c.exp_clip);
@@ -330,6 +332,7 @@ drc_blurz_bwd_kernel(const float *__restrict__ bgrid, const float *__restrict__ 
                      const float *__restrict__ g_voxels, float *__restrict__ g_grid,
                      float *__restrict__ scale_partials, int *__restrict__ zero_ints, int n_zero) {
   constexpr int W = 2 * R + 1, L = RingLen<R>::L;   // block length == ring length
+  pdl_release();          // head of the backward chain: launched without a programmatic edge
   if (zero_ints && blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kBwdThreads) zero_ints[i] = 0;
   constexpr int VV = V * V;
@@ -537,6 +540,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
   constexpr int VZ = V, W = 2 * R + 1, L = FwdRingLen<R>::L, VV = V * V;
   constexpr int NBLK = (VZ + L - 1) / L, NFULL = VZ / L, NSTORE = VZ > R ? (VZ - R) / L : 0;
   constexpr uint32_t ROW_BYTES = kBwdThreads * sizeof(u64);
+  pdl_release();          // head of the backward chain: launched without a programmatic edge
   if (zero_ints && blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += kBwdThreads) zero_ints[i] = 0;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -740,8 +744,8 @@ static void launch_fwd_vr(const DrcArgs &a, const RayConst &c, const Taps<R> &ta
   const int blocks = a.P * (V * V / 2) / kFwdThreads;
   const bool extra = voxels || probs;
 #define DPC_FWD(EX, SV, VZ, FS)                                                             \
-  blurz_drc_fwd_kernel<V, R, EX, SV, VZ, FS><<<blocks, kFwdThreads, 0, s>>>(                   \
-      a.grid, a.scale, c, taps, bsave, mask, depth, voxels, probs, a.tck, a.ck_slots)
+  launch_dep(blurz_drc_fwd_kernel<V, R, EX, SV, VZ, FS>, dim3(blocks), dim3(kFwdThreads), 0, s, \
+             a.grid, a.scale, c, taps, bsave, mask, depth, voxels, probs, a.tck, a.ck_slots)
   // the training configuration (cubic grid, no optional outputs, saved state) gets the
   // kernel with the depth as a compile-time constant
   // (a.tck: api.cu fast_ray_state() has checked cubic grid, log-sum DRC, no optional outputs)

@@ -93,6 +93,7 @@ pose_scatter_kernel(PoseArgs a, float *__restrict__ tr_pc, float *__restrict__ g
 template <bool WRITE_TRPC>
 __global__ void __launch_bounds__(kPoseThreads)
 pose_cells_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
+  pdl_release();          // head of the forward chain: launched without a programmatic edge
   const int b = blockIdx.y;
   const int n = blockIdx.x * kPoseThreads + threadIdx.x;
   const Quat q = block_quat(a.quat + 4 * b);
@@ -152,6 +153,8 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
   __shared__ unsigned cursor[kMaxBins + 1];
   const int b = blockIdx.y, tid = threadIdx.x;
   const unsigned rank = cluster.block_rank();
+  pdl_wait();             // the z-cell bytes and records come from pose_cells
+  pdl_release();
   const int n8 = cells.Npad / 8;                          // 8-byte groups of z-cell bytes
   const int per = (n8 + kBinSplit - 1) / kBinSplit;
   const int i_lo = rank * per, i_hi = min(n8, i_lo + per);
@@ -383,6 +386,8 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
                        const float *__restrict__ g_trpc, float *__restrict__ g_points,
                        double *__restrict__ partials, int *__restrict__ counters, FinalizeArgs fin,
                        CellsView cells, const float4 *__restrict__ part) {
+  pdl_wait();             // the per-plane partial gathers come from the blur-XY adjoint
+  pdl_release();
   const int b = blockIdx.y;
   const Quat q = block_quat(a.quat + 4 * b);
   const bool has_t = a.trans != nullptr;
@@ -584,8 +589,8 @@ int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const fl
   dim3 g(pose_partial_blocks(a.N), a.P), t(kBwdThreads);
   FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
                  g_quat, g_trans, g_focal, g_scale};
-  gather_pose_bwd_kernel<<<g, t, 0, s>>>(a, nullptr, g_trpc, g_points, partials, counters, f,
-                                         cells, part);
+  launch_dep(gather_pose_bwd_kernel, g, t, 0, s, a, (const float *)nullptr, g_trpc, g_points,
+             partials, counters, f, cells, part);
   return check_launch("pose_bwd_partials");
 }
 
@@ -600,7 +605,7 @@ int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, c
     pose_cells_kernel<true><<<g, t, 0, s>>>(a, tr_pc, cells);
   else
     pose_cells_kernel<false><<<g, t, 0, s>>>(a, tr_pc, cells);
-  bin_points_kernel<<<dim3(kBinSplit, a.P), kBinThreads, 0, s>>>(cells, a.N, a.Vz);
+  launch_dep(bin_points_kernel, dim3(kBinSplit, a.P), dim3(kBinThreads), 0, s, cells, a.N, a.Vz);
   return check_launch("pose_cells");
 }
 
