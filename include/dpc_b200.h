@@ -157,7 +157,9 @@ DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const floa
 /* How many chunks of projections dpc_project_fwd / dpc_project_bwd split this batch into (each
  * chunk is one set of kernel launches on one of two internal streams that fork from and join
  * `stream`): 2 half-batches for P >= 64, else 1; DPC_CHUNK=<projections> (environment)
- * overrides.  bench.py counts its launches with it. */
+ * overrides.  bench.py counts its launches with it.  Inside a chunk every kernel but the first
+ * is a programmatic dependent launch (it waits for its predecessor on the device with
+ * griddepcontrol.wait); DPC_PDL=0 (environment) launches them as plain stream-ordered kernels. */
 DPC_API int dpc_project_chunks(const dpc_params *p);
 
 /* Backward of the whole path.  g_grid is a [P,Vz,V,V] scratch buffer.

@@ -70,6 +70,9 @@ namespace dpc {
 #ifndef DPC_XY_UNROLL_FILL
 #define DPC_XY_UNROLL_FILL 1   // unroll factor of the tile fill
 #endif
+#ifndef DPC_XY_BITS_SMEM
+#define DPC_XY_BITS_SMEM 1     // backward: the plane's raw<=1 mask words are loaded at kernel entry
+#endif                         // and wait in shared memory (0: 16 global loads per thread at the end)
 // DPC_PROBE_FEW_FMA / _NO_SCATTER / _NO_FILL / _NO_MASK / _NO_GATHER: timing probes that leave one
 // phase out (WRONG results; used once to find out what the kernels' time is made of).
 
@@ -281,6 +284,21 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     touch = touch_range(cells, pb, pz, N);
     rec0 = first_touching_record(touch, tid);
   }
+  // backward: this plane's clamp-gate words (V*V/32 of them, one or two per thread) are requested
+  // now and parked in shared memory behind everything else once the tile fill has been issued --
+  // the masking at the very end of the kernel then finds them on chip
+  constexpr bool BITS_SMEM = MASK_OUT && DPC_XY_BITS_SMEM;
+  constexpr int MWORDS = V * V / 32, MW = (MWORDS + C::THREADS - 1) / C::THREADS;
+  uint32_t *mask_s = reinterpret_cast<uint32_t *>(
+      reinterpret_cast<unsigned char *>(smem2) + C::SMEM +
+      ((POINTS && MASK_OUT && C::YTASKS != C::THREADS) ? V * V * 4 : 0));
+  uint32_t mword[MW];
+  if (BITS_SMEM) {
+#pragma unroll
+    for (int i = 0; i < MW; ++i)
+      mword[i] = tid + i * C::THREADS < MWORDS
+                     ? __ldg(bits_in + plane * MWORDS + tid + i * C::THREADS) : 0u;
+  }
   // (pads only: measured 498 -> 484 us at 128^2, but 43.0 -> 46.7 us at 64^2, where the whole
   // tile is 11 vector stores per thread)
   // fixed-point plane scatter (one-tile layouts): the tile starts as the bias 1.0f, pads included,
@@ -387,6 +405,11 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
         d[2] = make_float2(a.z, b.z);
         d[3] = make_float2(a.w, b.w);
       }
+    }
+    if (BITS_SMEM && h == 0) {
+#pragma unroll
+      for (int i = 0; i < MW; ++i)
+        if (tid + i * C::THREADS < MWORDS) mask_s[tid + i * C::THREADS] = mword[i];
     }
     __syncthreads();
     // ---- X pass: lanes <-> consecutive row pairs, one 16-wide x block ----
@@ -496,7 +519,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       bx_unpack2(acc[j], lo, hi);
 #ifndef DPC_PROBE_NO_MASK
       if (MASK_OUT) {
-        const uint32_t wbits = __ldg(bits_in + plane * (V * V / 32) + ((y0 + j) * V + 2 * cp) / 32);
+        const uint32_t wbits = BITS_SMEM ? mask_s[((y0 + j) * V + 2 * cp) / 32]
+                                         : __ldg(bits_in + plane * MWORDS + ((y0 + j) * V + 2 * cp) / 32);
         const uint32_t sh = (2 * cp) & 31;
         lo = ((wbits >> sh) & 1u) ? lo : 0.f;
         hi = ((wbits >> (sh + 1)) & 1u) ? hi : 0.f;
@@ -539,7 +563,7 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
   do {                                                                                         \
     /* the gather tile lives behind the window tiles when it cannot overlay them */            \
     const size_t smem = C::SMEM + ((PT && MO && C::YTASKS != C::THREADS) ? V * V * 4 : 0) +    \
-                        ((PT && WB) ? C::RH * V / 8 : 0);                                      \
+                        ((PT && WB) ? C::RH * V / 8 : 0) + ((MO && DPC_XY_BITS_SMEM) ? V * V / 8 : 0); \
     static DeviceOnce attr_once;                                                               \
     if (attr_once.first()) {                                                                   \
       cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT>,                               \

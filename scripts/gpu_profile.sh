@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU call: the ncu evidence for profiles/ (B200_PROFILING.md recipe).
+#   1. the bench command exits 0 without ncu, then its launch list (gpu__time_duration per launch)
+#   2. one `--set full` capture of a whole-batch step (DPC_CHUNK=P: one launch per kernel)
+# usage: bash scripts/gpu_profile.sh <tag>     -> gpurun_out/launches_<tag>.csv, prof_<tag>.ncu-rep
+tag=${1:-rxx}
+mkdir -p gpurun_out
+BENCH="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+$BENCH > gpurun_out/bench_$tag.json 2> gpurun_out/bench_${tag}_err.log || { echo "bench failed"; tail -5 gpurun_out/bench_${tag}_err.log; exit 1; }
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file gpurun_out/launches_$tag.csv $BENCH > gpurun_out/ncu_$tag.log 2>&1
+echo "launch list rc=$? lines=$(wc -l < gpurun_out/launches_$tag.csv)"
+DPC_CHUNK=100000 python scripts/profile_step.py --steps 2 > gpurun_out/plain_$tag.log 2>&1 || { echo "profile_step failed"; exit 1; }
+DPC_CHUNK=100000 timeout 600 ncu --set full --clock-control none --import-source on -f \
+    -o gpurun_out/prof_$tag python scripts/profile_step.py --steps 2 > gpurun_out/ncu_full_$tag.log 2>&1
+echo "full capture rc=$?"; ls -la gpurun_out/prof_$tag.ncu-rep
