@@ -46,9 +46,19 @@ def dpc():
     return m
 
 
-@pytest.mark.parametrize("i", range(24))
+def draw128(i):
+    """Paper-scale grid (128^3; vox_size_z 128 or 96), small batches: a pure function of i."""
+    r = random.Random(9500 + i)
+    return dict(V=128, vz=r.choice([-1, -1, 96]), K=r.choice([1, 5, 11, 15, 21]),
+                sigma=r.uniform(0.3, 3.0), P=r.choice([1, 2]), N=r.choice([100, 3001, 16000]),
+                kind=r.choice(["uniform", "clustered"]), translation=r.random() < 0.5,
+                focal=r.random() < 0.5, scale=r.random() < 0.7, logsum=r.random() < 0.8,
+                outputs=r.random() < 0.5, deterministic=r.random() < 0.3, no_blur=False)
+
+
+@pytest.mark.parametrize("i", list(range(24)) + [128 + k for k in range(4)])
 def test_random_draw_matches_oracle(dpc, i):
-    d = draw(i)
+    d = draw(i) if i < 128 else draw128(i - 128)
     cfg = default_cfg(vox_size=d["V"], vox_size_z=d["vz"], pc_gauss_kernel_size=d["K"],
                       drc_logsum=d["logsum"])
     case = _inputs.make_case(cfg, d["P"], d["N"], 7000 + i, kind=d["kind"],
