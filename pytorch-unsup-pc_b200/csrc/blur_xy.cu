@@ -70,6 +70,9 @@ namespace dpc {
 #ifndef DPC_XY_UNROLL_FILL
 #define DPC_XY_UNROLL_FILL 1   // unroll factor of the tile fill
 #endif
+#ifndef DPC_XY_SKIP_EMPTY
+#define DPC_XY_SKIP_EMPTY 1    // planes no point touches: zeros forward, nothing backward
+#endif
 #ifndef DPC_XY_BITS_SMEM
 #define DPC_XY_BITS_SMEM 1     // backward: the plane's raw<=1 mask words are loaded at kernel entry
 #endif                         // and wait in shared memory (0: 16 global loads per thread at the end)
@@ -283,6 +286,17 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   if (POINTS && DPC_XY_PREFETCH) {
     touch = touch_range(cells, pb, pz, N);
     rec0 = first_touching_record(touch, tid);
+  }
+  // A plane no point touches (real clouds fill a fraction of the frustum's depth): forward, its
+  // raw occupancy is zero, so both blur passes give zero and every raw <= 1 bit is set; backward,
+  // nobody gathers from it, so there is nothing to compute at all.
+  if (POINTS && DPC_XY_PREFETCH && DPC_XY_SKIP_EMPTY && touch.hi == touch.lo) {
+    if (WRITE_BITS) {
+      float4 *dz4 = reinterpret_cast<float4 *>(dst + plane * V * V);
+      for (int i = tid; i < V * V / 4; i += C::THREADS) dz4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < V * V / 32; i += C::THREADS) bits_out[plane * (V * V / 32) + i] = 0xffffffffu;
+    }
+    return;
   }
   // backward: this plane's clamp-gate words (V*V/32 of them, one or two per thread) are requested
   // now and parked in shared memory behind everything else once the tile fill has been issued --

@@ -1,5 +1,7 @@
 """Per-stage CUDA-event timings of one projection step through dpc_project_profile (dev helper
-for kernel A/B runs: DPC_B200_LIB=<variant .so> python scripts/stage_time.py [A|B] [iters])."""
+for kernel A/B runs: DPC_B200_LIB=<variant .so> python scripts/stage_time.py [A|B] [iters] [box]).
+`box` < 0.9 shrinks the synthetic clouds to a cube of that side (an object that fills part of
+the frustum: planes of depth no point touches)."""
 import ctypes
 import os
 import sys
@@ -12,7 +14,7 @@ import pytorch_unsup_pc_b200 as dpc
 from pytorch_unsup_pc_b200 import _lib, ops
 
 
-def main(workload="A", iters=30):
+def main(workload="A", iters=30, box=0.9):
     w = bench.WORKLOADS[workload]
     cfg = bench.make_cfg(w)
     lib = _lib.load()
@@ -22,6 +24,7 @@ def main(workload="A", iters=30):
     taps = ops.host_taps(dpc.smoothing_kernel(cfg, w["sigma"]))
     params = ops.make_params(cfg, P, N, flip_y=True)
     d = {k: v.to(dev) for k, v in bench.synth_inputs(w, 1000).items()}
+    d["points"] = d["points"] * (box / 0.9)
     f32 = dict(dtype=torch.float32, device=dev)
     buf = dict(tr_pc=torch.empty(P, N, 3, **f32), grid=torch.empty(P, Vz, V, V, **f32),
                bits=torch.empty(P, Vz, V, V // 32, dtype=torch.int32, device=dev),
@@ -44,9 +47,9 @@ def main(workload="A", iters=30):
     torch.cuda.synchronize()
     t = {k: round(float(v) * 1e3, 1) for k, v in zip(_lib.PROFILE_STAGES, stage_ms)}
     chk = [float(buf[k].double().abs().sum()) for k in ("mask", "depth", "g_points", "g_quat", "g_scale")]
-    print(os.path.basename(_lib.LIB_PATH), workload, t, "sum %.1f" % sum(t.values()),
+    print(os.path.basename(_lib.LIB_PATH), workload, "box %.2f" % box, t, "sum %.1f" % sum(t.values()),
           "chk", " ".join("%.6e" % c for c in chk))
 
 
 if __name__ == "__main__":
-    main(*(sys.argv[1:2] or ["A"]), *[int(x) for x in sys.argv[2:3]])
+    main(*(sys.argv[1:2] or ["A"]), *[int(x) for x in sys.argv[2:3]], *[float(x) for x in sys.argv[3:4]])

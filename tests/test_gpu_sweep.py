@@ -78,3 +78,26 @@ def test_random_draw_matches_oracle(dpc, i):
         assert v < FWD_TOL, (d, k, v)
     for k, v in gerrs.items():
         assert v < GRAD_TOL, (d, k, v)
+
+
+@pytest.mark.parametrize("V,outputs", [(64, True), (64, False), (32, False), (128, False)])
+def test_thin_slab_leaves_most_planes_empty(dpc, V, outputs):
+    """A cloud confined to a thin slab of depth: a third or more of the Z-planes are touched by no point (the
+    plane kernels skip them: zeros forward, nothing to gather backward).  Identity-like poses keep
+    the slab thin after the camera transform."""
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=21)
+    P, N = 3, 4000
+    case = _inputs.make_case(cfg, P, N, 4242 + V, translation=True, screened=False)
+    case["points"][..., 0] = 0.04 * case["points"][..., 0] + 0.1      # depth within ~0.04 of 0.1
+    case["quat"] = torch.tensor([[1.0, 0.01, -0.02, 0.015]]).repeat(P, 1) * torch.tensor([[1.0], [2.0], [0.5]])
+    case["points"] = _inputs.screen(cfg, case, torch.Generator().manual_seed(1))
+    case["kernel"] = CF.smoothing_taps(cfg, 2.0)
+    o_out, _, o_grads = run_oracle(cfg, case, P, V)
+    raw = CF.scatter_trilinear(cfg, o_out["tr_pc"])
+    assert (raw.detach().reshape(P, -1, V * V).abs().sum(-1) == 0).float().mean() > 0.3   # many empty planes
+    with dpc.options(voxels=outputs, drc_probs=outputs):
+        c_out, _, c_grads = run_cuda(dpc, cfg, case, P, V)
+    for k in ("proj", "proj_depth", "tr_pc") + (("voxels", "drc_probs") if outputs else ()):
+        assert _golden.rel_err(c_out[k], o_out[k]) < FWD_TOL, k
+    for k in o_grads:
+        assert _golden.rel_err(c_grads[k], o_grads[k]) < GRAD_TOL, k
