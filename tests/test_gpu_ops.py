@@ -132,6 +132,34 @@ def test_no_cpu_fallback(dpc):
         dpc.pointcloud_project_fast(cfg, torch.zeros(1, 4, 3), torch.ones(1, 4), None, None)
 
 
+def test_plain_launches_give_the_same_bits(dpc):
+    """DPC_PDL=0 (read once per process) launches the chain's kernels as plain stream-ordered
+    kernels instead of programmatic dependent launches: a fresh process computes one projection
+    step both ways and the outputs and gradients must be the same bits."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "import pytorch_unsup_pc_b200 as dpc\n"
+        "cfg = dpc.default_cfg(vox_size=64, pc_gauss_kernel_size=21)\n"
+        "g = torch.Generator().manual_seed(77)\n"
+        "p = ((torch.rand(66, 3000, 3, generator=g) - 0.5) * 0.9).cuda().requires_grad_()\n"
+        "q = torch.randn(66, 4, generator=g).cuda().requires_grad_()\n"
+        "o = dpc.pointcloud_project_fast(cfg, p, q, None, None, dpc.smoothing_kernel(cfg, 3.0))\n"
+        "gp, gq = torch.autograd.grad(o['proj'].sum() + o['proj_depth'].sum(), [p, q])\n"
+        "print(' '.join(repr(float(t.double().sum())) for t in (o['proj'], o['proj_depth'], gp, gq)))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for pdl in ("1", "0"):
+        env = dict(os.environ, DPC_PDL=pdl)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
+
+
 def test_full_size_properties(dpc):
     """Microbench shapes (P=64, N=8000, 64^3, K=21): size-independent properties."""
     cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
