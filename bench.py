@@ -533,7 +533,8 @@ def run_b200(args, rank, world, local_rank):
         # kernels per chunk: pose_cells + bin_points (or pose_scatter), blur_xy, blurz_drc_fwd |
         # drc_blurz_bwd, blur_xy, gather_pose_bwd -- times the chunks the batch is split into
         # (whole job: every rank launches its own)
-        "gpu_launches": (6 if args.global_grid else 7) * n_chunks * args.steps * world,
+        "gpu_launches": (6 if args.global_grid else lib.dpc_project_kernels_per_chunk(
+            ctypes.byref(params))) * n_chunks * args.steps * world,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (None if args.global_grid else

@@ -162,6 +162,11 @@ DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const floa
  * griddepcontrol.wait); DPC_PDL=0 (environment) launches them as plain stream-ordered kernels. */
 DPC_API int dpc_project_chunks(const dpc_params *p);
 
+/* Kernel launches of one chunk's forward + backward on the default (plane-local) path: 6 when
+ * the pose and the z-binning of the points run as one cluster kernel (N <= 16384), 7 otherwise.
+ * bench.py's gpu_launches = this x dpc_project_chunks x steps. */
+DPC_API int dpc_project_kernels_per_chunk(const dpc_params *p);
+
 /* Backward of the whole path.  g_grid is a [P,Vz,V,V] scratch buffer.
  * Upstream grads: g_mask, g_depth [P,V,V]; g_probs, g_voxels, g_tr_pc optional.
  * Outputs: g_points [P,N,3], g_quat [P,4]; g_trans [P,3], g_focal [P],

@@ -42,6 +42,7 @@ SIGNATURES = {
     "dpc_workspace_bytes": [_P],
     "dpc_cells_bytes": [_P],
     "dpc_project_chunks": [_P],
+    "dpc_project_kernels_per_chunk": [_P],
     "dpc_pose_fwd": [_P] + [c_void_p] * 5 + [c_void_p],
     "dpc_pose_bwd": [_P] + [c_void_p] * 9 + [c_void_p, c_size_t, c_void_p],
     "dpc_scatter_fwd": [_P, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],

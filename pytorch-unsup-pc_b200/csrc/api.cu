@@ -394,6 +394,13 @@ int dpc_project_chunks(const dpc_params *p) {
   return c < p->P ? (p->P + c - 1) / c : 1;
 }
 
+int dpc_project_kernels_per_chunk(const dpc_params *p) {
+  if (!p || p->N < 1) return 0;
+  // forward: pose (+ binning) | [binning] | plane scatter + blur XY | blur Z + DRC;
+  // backward: DRC + blur Z adjoint | blur XY adjoint + plane gather | pose adjoint
+  return pose_bin_split(p->N) > 0 ? 6 : 7;
+}
+
 struct FwdPtrs {
   const float *points, *quat, *trans, *focal, *scale;
   float *tr_pc, *grid_b; uint32_t *bits; float *mask, *depth, *voxels, *probs;

@@ -171,6 +171,7 @@ inline CellsView cells_view(void *base, int P, int N, int Vz) {
 }
 // pose -> tr_pc (NULL ok) + cell records
 int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, cudaStream_t s);
+int pose_bin_split(int N);   // > 0: pose + binning run as one cluster kernel of that many CTAs per projection
 // pose adjoint fed by the two per-plane partial gathers of the fused blur-XY
 // adjoint (part[dz][P][N] float4 = dL/du contribution of the corners in plane
 // iz + dz) + fused last-block finalize

@@ -18,6 +18,7 @@
 // translation / focal partial sums into a fixed-order two-stage reduction, so
 // every gradient is deterministic.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "pose.cuh"
@@ -31,7 +32,10 @@ static int point_blocks(int N) { return (N + kPoseThreads - 1) / kPoseThreads; }
 // the pose adjoint: kBwdThreads threads x kBwdPts points each per CTA, one row of
 // 8 fp64 partial sums per CTA
 constexpr int kBwdThreads = 128;
-constexpr int kBwdPts = 4;
+#ifndef DPC_BWD_PTS
+#define DPC_BWD_PTS 4          // points per thread of the pose adjoint (A/B)
+#endif
+constexpr int kBwdPts = DPC_BWD_PTS;
 int pose_partial_blocks(int N) { return (N + kBwdThreads * kBwdPts - 1) / (kBwdThreads * kBwdPts); }
 
 // The normalised quaternion of the CTA's projection, computed by ONE thread (a double-precision
@@ -222,6 +226,122 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
       if (c != kCellNone) srec[atomicAdd(&cursor[c], 1u)] = __ldg(rec + 8 * i + k);
     }
   }
+}
+
+// Pose + cell records + counting sort in ONE launch (the default forward point kernel).
+// pose_cells_kernel -> bin_points_kernel is a chain of two latency-bound launches at the head of
+// every forward pass, where nothing else of the step can overlap them: the records travel to
+// global memory and back, and the second kernel starts with a cold read of them.  Here the cluster
+// that sorts a projection's records also computes them: every thread derives the pose, tr_pc and
+// cell of up to kFuseIter points, keeps their records in REGISTERS while the cluster builds and
+// exchanges its histograms (same scheme as bin_points_kernel), and then places them.  The
+// unsorted record array is never written.  The kernel is a latency chain (points -> fp64 pose
+// -> histogram -> two cluster barriers -> placement), so a thread gets as FEW points as a
+// portable cluster (<= 8 CTAs of 256 threads) allows: ITER = 2 up to 4096 points, 4 up to 8192,
+// 8 up to 16384 (measured at N = 8000, whole batch: the two kernels 21.9 us; 8 points per thread
+// in 4 CTAs of 256: 18.4 us; 4 points in 8 CTAs of 256: 15.5 us; 2 points in 8 CTAs of 512:
+// 19.4 us); larger clouds take the two kernels above.  Same device functions, same roundings:
+// identical records.
+#ifndef DPC_FUSE_THREADS
+#define DPC_FUSE_THREADS 256   // threads per CTA (512: slower, the barriers grow with the CTA)
+#endif
+constexpr int kFuseThreads = DPC_FUSE_THREADS;
+constexpr int kFuseMaxSplit = 8;               // portable cluster size
+template <bool WRITE_TRPC, int ITER>
+__global__ void __launch_bounds__(kFuseThreads)
+pose_bin_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
+  constexpr int kFuseIter = ITER;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ unsigned hist[kMaxBins];
+  __shared__ unsigned ahead[kMaxBins];
+  __shared__ unsigned cursor[kMaxBins + 1];
+  pdl_release();          // head of the forward chain: launched without a programmatic edge
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const unsigned rank = cluster.block_rank(), nsplit = cluster.num_blocks();
+  for (int i = tid; i < kMaxBins; i += kFuseThreads) hist[i] = 0;
+  const Quat q = block_quat(a.quat + 4 * b);     // (ends with a barrier: hist is zero behind it)
+  const bool has_t = a.trans != nullptr;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  if (has_t) {
+    t0 = a.trans[3 * b];
+    t1 = a.trans[3 * b + 1];
+    t2 = a.trans[3 * b + 2];
+  }
+  const double f = a.focal ? (double)a.focal[b] : a.focal_const;
+  uint8_t *czg = cells.cellz + (size_t)b * cells.Npad;
+  const int lo = (int)rank * (kFuseIter * kFuseThreads);
+  uint4 rec[kFuseIter];
+  unsigned cz[kFuseIter];
+#pragma unroll
+  for (int it = 0; it < kFuseIter; ++it) {
+    const int n = lo + it * kFuseThreads + tid;
+    cz[it] = kCellNone;
+    rec[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (n < a.N) {
+      const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+      const PosePoint pp = pose_point(q, a.points[si], a.points[si + 1], a.points[si + 2], has_t,
+                                      t0, t1, t2, f, a.cam_dist);
+      if (WRITE_TRPC) {
+        tr_pc[pi] = (float)pp.u0;
+        tr_pc[pi + 1] = (float)pp.u1;
+        tr_pc[pi + 2] = (float)pp.u2;
+      }
+      const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
+      if (c.valid) {
+        cz[it] = (unsigned)c.iz;
+        rec[it] = make_uint4(((unsigned)n << 16) | ((unsigned)c.iy << 8) | (unsigned)c.ix,
+                             __float_as_uint((float)c.rz), __float_as_uint((float)c.ry),
+                             __float_as_uint((float)c.rx));
+        atomicAdd(&hist[c.iz], 1u);
+      }
+    }
+    if (n < cells.Npad) czg[n] = (uint8_t)cz[it];     // the backward reads the z cell per point
+  }
+  cluster.sync();
+  for (int z = tid; z < kMaxBins; z += kFuseThreads) {
+    unsigned total = 0, before = 0;
+    if (z < a.Vz) {
+      for (unsigned r = 0; r < nsplit; ++r) {
+        const unsigned v = *cluster.map_shared_rank(&hist[z], r);
+        total += v;
+        before += r < rank ? v : 0u;
+      }
+    }
+    cursor[z] = total;
+    ahead[z] = before;
+  }
+  cluster.sync();               // no CTA may exit while its histogram can still be read
+  if (tid < 32) {
+    constexpr int PER = kMaxBins / 32;
+    unsigned v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      v[k] = cursor[tid * PER + k];
+      sum += v[k];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += t;
+    }
+    unsigned run = incl - sum;
+    uint32_t *bs = cells.binstart + (size_t)b * cells.zstride;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int z = tid * PER + k;
+      if (rank == 0 && z <= a.Vz) bs[z] = run;            // z == Vz: the total
+      cursor[z] = run + ahead[z];
+      run += v[k];
+    }
+    if (rank == 0 && tid == 31 && a.Vz == kMaxBins) bs[a.Vz] = run;
+  }
+  __syncthreads();
+  uint4 *srec = cells.srec + (size_t)b * a.N;
+#pragma unroll
+  for (int it = 0; it < kFuseIter; ++it)
+    if (cz[it] != kCellNone) srec[atomicAdd(&cursor[cz[it]], 1u)] = rec[it];
 }
 
 __global__ void __launch_bounds__(kPoseThreads)
@@ -594,6 +714,7 @@ int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const fl
   return check_launch("pose_bwd_partials");
 }
 
+static int pose_bin_iter(int N);
 int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, cudaStream_t s) {
   dim3 g((cells.Npad + kPoseThreads - 1) / kPoseThreads, a.P), t(kPoseThreads);
   if (a.Vz > kMaxBins || a.N > 65535 || a.V > 256) {
@@ -601,12 +722,55 @@ int launch_pose_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, c
               kMaxBins);
     return DPC_ERR_ARG;
   }
+  const int split = pose_bin_split(a.N);
+  if (split > 0) {
+    // one launch: a cluster of `split` CTAs per projection (runtime cluster dimension)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(split, a.P);
+    cfg.blockDim = dim3(kFuseThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = split;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int iter = pose_bin_iter(a.N);
+#define DPC_POSE_BIN(TR, IT) cudaLaunchKernelEx(&cfg, pose_bin_kernel<TR, IT>, a, tr_pc, cells)
+    if (tr_pc) {
+      if (iter == 2) DPC_POSE_BIN(true, 2); else if (iter == 4) DPC_POSE_BIN(true, 4); else DPC_POSE_BIN(true, 8);
+    } else {
+      if (iter == 2) DPC_POSE_BIN(false, 2); else if (iter == 4) DPC_POSE_BIN(false, 4); else DPC_POSE_BIN(false, 8);
+    }
+#undef DPC_POSE_BIN
+    return check_launch("pose_bin");
+  }
   if (tr_pc)
     pose_cells_kernel<true><<<g, t, 0, s>>>(a, tr_pc, cells);
   else
     pose_cells_kernel<false><<<g, t, 0, s>>>(a, tr_pc, cells);
   launch_dep(bin_points_kernel, dim3(kBinSplit, a.P), dim3(kBinThreads), 0, s, cells, a.N, a.Vz);
   return check_launch("pose_cells");
+}
+
+// CTAs per projection of the fused pose + binning kernel; 0: the cloud is too large for it (or
+// DPC_FUSED_BIN=0 in the environment, for A/B runs) and the two-kernel path runs
+// points per thread of the fused kernel: the smallest of 2 / 4 / 8 that fits one portable cluster
+static int pose_bin_iter(int N) {
+  const int npad = cells_npad(N);
+  for (int it = 2; it <= 8; it *= 2)
+    if (npad <= it * kFuseThreads * kFuseMaxSplit) return it;
+  return 0;
+}
+int pose_bin_split(int N) {
+  static const bool off = getenv("DPC_FUSED_BIN") && atoi(getenv("DPC_FUSED_BIN")) == 0;
+  const int it = pose_bin_iter(N);
+  if (off || it == 0) return 0;
+  const int need = (cells_npad(N) + it * kFuseThreads - 1) / (it * kFuseThreads);
+  int split = 1;
+  while (split < need) split *= 2;
+  return split;
 }
 
 int launch_gather_trpc_bwd(const float *tr_pc, int P, int N, int Vz, int V, const float *g_grid,
