@@ -4,8 +4,9 @@ inputs, no CUDA graph) -- the command ncu wraps (B200_PROFILING.md):
 
     python scripts/profile_step.py [--workload A|B] [--steps 3] [--global-grid] [--P n] [--N n]
 
-Each step launches, in order: pose_cells, blur_xy (plane scatter), blurz_drc_fwd,
-drc_blurz_bwd, blur_xy (plane gather), gather_pose_bwd  -> 6 kernels per step.
+Each step launches, in order: pose_bin (pose + z-binning), blur_xy (plane scatter),
+blurz_drc_fwd, drc_blurz_bwd_fast, blur_xy (plane gather), gather_pose_bwd -> 6 kernels per
+chunk and step (DPC_CHUNK=<P or more>: one chunk).
 """
 import argparse
 import ctypes
