@@ -77,9 +77,9 @@ def stage_algorithmic_bytes(N, V, Vz):
 # flushes the caches before every replay).  None = not captured for that workload.
 NCU_CAPTURE = "profiles/r01_ncu_full_step_pdl.csv"
 NCU_TRAFFIC_BYTES = {
-    "A": {"pose_scatter": 6.16e6 + 0.0 + 8.72e6, "blur_xy_fwd": 7.47e6 + 13.83e6,
-          "blurz_drc_fwd": 67.15e6 + 15.99e6, "drc_blurz_bwd": 71.35e6 + 21.97e6,
-          "blur_xy_bwd": 77.20e6 + 4.40e6, "gather_pose_bwd": 23.12e6 + 0.0},
+    "A": {"pose_scatter": 6.18e6 + 0.0, "blur_xy_fwd": 7.47e6 + 11.24e6,
+          "blurz_drc_fwd": 67.15e6 + 12.97e6, "drc_blurz_bwd": 71.36e6 + 23.46e6,
+          "blur_xy_bwd": 77.02e6 + 3.43e6, "gather_pose_bwd": 23.12e6 + 0.0},
 }
 
 
