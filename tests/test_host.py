@@ -38,6 +38,23 @@ def test_workspace_bytes_and_params_struct():
     assert need % 256 == 0
 
 
+def test_launch_plan_queries():
+    """Host-side launch plan (no GPU needed): half-batches from 64 projections on, and 6 kernel
+    launches per chunk while the cloud fits the fused pose + binning cluster kernel (N <= 16384),
+    7 beyond."""
+    from pytorch_unsup_pc_b200 import _lib, ops
+    lib = _lib.load()
+    cfg = default_cfg(vox_size=64)
+    plan = lambda P, N: (lib.dpc_project_chunks(ctypes.byref(ops.make_params(cfg, P, N))),
+                         lib.dpc_project_kernels_per_chunk(ctypes.byref(ops.make_params(cfg, P, N))))
+    assert plan(64, 8000) == (2, 6)
+    assert plan(63, 8000) == (1, 6)
+    assert plan(65, 1) == (1, 6)
+    assert plan(128, 16384) == (2, 6)
+    assert plan(4, 16385) == (1, 7)
+    assert plan(4, 65535) == (1, 7)
+
+
 def test_cpu_tensors_are_refused():
     import pytorch_unsup_pc_b200 as dpc
     cfg = default_cfg(vox_size=32)
