@@ -530,8 +530,9 @@ def run_b200(args, rank, world, local_rank):
             "note": "informational: the same device-resident steps issued as two independent "
                     "streams of batches (two graphs, two streams, replayed alternately); `value` "
                     "is the one-stream figure"},
-        # kernels per chunk: pose_cells + bin_points (or pose_scatter), blur_xy, blurz_drc_fwd |
-        # drc_blurz_bwd, blur_xy, gather_pose_bwd -- times the chunks the batch is split into
+        # kernels per chunk: pose_bin (pose_cells + bin_points above 16384 points; pose_scatter on
+        # the global-grid path), blur_xy, blurz_drc_fwd | drc_blurz_bwd, blur_xy, gather_pose_bwd
+        # -- times the chunks the batch is split into
         # (whole job: every rank launches its own)
         "gpu_launches": (6 if args.global_grid else lib.dpc_project_kernels_per_chunk(
             ctypes.byref(params))) * n_chunks * args.steps * world,
