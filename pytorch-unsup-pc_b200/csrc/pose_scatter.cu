@@ -31,7 +31,10 @@ constexpr int kPoseThreads = 256;
 static int point_blocks(int N) { return (N + kPoseThreads - 1) / kPoseThreads; }
 // the pose adjoint: kBwdThreads threads x kBwdPts points each per CTA, one row of
 // 8 fp64 partial sums per CTA
-constexpr int kBwdThreads = 128;
+#ifndef DPC_BWD_PT_THREADS
+#define DPC_BWD_PT_THREADS 128 // threads per CTA of the pose adjoint (A/B)
+#endif
+constexpr int kBwdThreads = DPC_BWD_PT_THREADS;
 #ifndef DPC_BWD_PTS
 #define DPC_BWD_PTS 4          // points per thread of the pose adjoint (A/B)
 #endif
