@@ -205,9 +205,9 @@ struct TouchRange {
 __device__ __forceinline__ TouchRange touch_range(const CellsView &cells, int b, int z, int N) {
   const uint32_t *bs = cells.binstart + (size_t)b * cells.zstride;
   TouchRange t;
-  t.mid = __ldg(bs + z);
-  t.hi = __ldg(bs + z + 1);
-  t.lo = z > 0 ? __ldg(bs + z - 1) : t.mid;
+  t.mid = ld_dep(bs + z);
+  t.hi = ld_dep(bs + z + 1);
+  t.lo = z > 0 ? ld_dep(bs + z - 1) : t.mid;
   t.srec = cells.srec + (size_t)b * N;
   return t;
 }
@@ -218,10 +218,10 @@ __device__ __forceinline__ void for_each_touching_point(const TouchRange &t, int
                                                         const uint4 first, F &&f) {
   uint32_t i = t.lo + tid;
   if (i < t.hi) f(first, i < t.mid ? 1 : 0);
-  for (i += nthreads; i < t.hi; i += nthreads) f(__ldg(t.srec + i), i < t.mid ? 1 : 0);
+  for (i += nthreads; i < t.hi; i += nthreads) f(ld_dep(t.srec + i), i < t.mid ? 1 : 0);
 }
 __device__ __forceinline__ uint4 first_touching_record(const TouchRange &t, int tid) {
-  return t.lo + tid < t.hi ? __ldg(t.srec + t.lo + tid) : make_uint4(0u, 0u, 0u, 0u);
+  return t.lo + tid < t.hi ? ld_dep(t.srec + t.lo + tid) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Shared-memory float add that returns the NEW value (fp32 shared atomics are a
@@ -246,13 +246,20 @@ __device__ __forceinline__ float smem_add_new(float *p, float w) {
 // four serial compare-and-swap loops, and integer adds commute: the plane no longer depends on
 // the order in which points arrive, so the default path is bit-reproducible run to run.
 // raw > 1  <=>  bits > bits(2.0f) (positive floats order like their bit patterns); elements that
-// are already past 2.0 are left alone, which bounds the sum far below the next binade overflow.
+// are already past 2.0 are left alone, and every add that lands past 2.0 is followed by an
+// atomicMin back to the first pattern above it: the check and the add are two operations, so a
+// pile of threads may all pass the check and add on top of each other, but the element ENDS at a
+// pattern in (2.0, 2.0 + 2^-22] whatever the interleaving (decoded as raw > 1 -> clamp gives 1),
+// never in the Inf/NaN or sign-bit range.  (The transient sum wraps 2^32 only past 384 in-flight
+// adds of weight 1 to one element -- more than three quarters of the largest CTA.)
 constexpr uint32_t kFixOne = 0x3F800000u, kFixTwo = 0x40000000u;
 __device__ __forceinline__ bool scatter_add_fixed(float *p, float w) {   // true: element now > 1
   uint32_t *ip = reinterpret_cast<uint32_t *>(p);
   if (*reinterpret_cast<volatile uint32_t *>(ip) > kFixTwo) return false;   // saturated before
   const uint32_t wq = __float2uint_rn(w * 8388608.f);
-  return atomicAdd(ip, wq) + wq > kFixTwo;
+  if (atomicAdd(ip, wq) + wq <= kFixTwo) return false;
+  atomicMin(ip, kFixTwo + 1u);
+  return true;
 }
 
 __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
@@ -390,8 +397,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #ifdef DPC_PROBE_NO_FILL
       float4 a = make_float4(0.f, 1.f, 0.f, 1.f), b = a;
 #else
-      float4 a = __ldg(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
-      float4 b = __ldg(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
+      float4 a = ld_dep(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
+      float4 b = ld_dep(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
 #endif
       if (WRITE_BITS) {
         uint32_t na = le1_nibble(a) << (4 * (tid & 7)), nb = le1_nibble(b) << (4 * (tid & 7));

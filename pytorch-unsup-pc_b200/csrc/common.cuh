@@ -79,6 +79,13 @@ struct DeviceOnce {
 // DPC_PDL=0 (env) launches the same kernels without the attribute (A/B).
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Load of data that the programmatic primary (the kernel this one waits for) may have written:
+// a COHERENT load (ld.global.cg, L2) -- never ld.global.nc (__ldg), whose contract is that the
+// data is read-only for the whole lifetime of the reading grid, and under a programmatic launch
+// this grid is already resident while the primary is still writing.  __ldg stays on true inputs
+// (points, taps, upstream gradients, the forward's saved state in the backward).
+template <typename T>
+__device__ __forceinline__ T ld_dep(const T *p) { return __ldcg(p); }
 #ifndef DPC_PDL_EARLY
 #define DPC_PDL_EARLY 0
 #endif
@@ -121,7 +128,10 @@ struct PoseArgs {
 // float offset of point n of projection b in a.points
 __device__ __forceinline__ size_t point_offset(const PoseArgs &a, int b, int n) {
   if (a.replicas == 0) return ((size_t)b * a.N + n) * 3;
-  const int src = a.sel ? __ldg(a.sel + (size_t)b * a.N + n) : n;
+  int src = a.sel ? __ldg(a.sel + (size_t)b * a.N + n) : n;
+  // the Python mirror validates a user-supplied selection; a raw C-ABI caller's bad index is
+  // clamped into the cloud so that it can never become an out-of-bounds read
+  src = min(max(src, 0), a.N_src - 1);
   return ((size_t)(b / a.replicas) * a.N_src + src) * 3;
 }
 #endif

@@ -171,7 +171,7 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
   for (int i = tid; i < kMaxBins; i += kBinThreads) hist[i] = 0;
   __syncthreads();
   for (int i = i_lo + tid; i < i_hi; i += kBinThreads) {
-    const uint2 w = __ldg(cz + i);
+    const uint2 w = ld_dep(cz + i);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const unsigned c = ((k < 4 ? w.x : w.y) >> (8 * (k % 4))) & 0xFFu;
@@ -222,11 +222,11 @@ bin_points_kernel(CellsView cells, int N, int Vz) {
   }
   __syncthreads();
   for (int i = i_lo + tid; i < i_hi; i += kBinThreads) {
-    const uint2 w = __ldg(cz + i);
+    const uint2 w = ld_dep(cz + i);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const unsigned c = ((k < 4 ? w.x : w.y) >> (8 * (k % 4))) & 0xFFu;
-      if (c != kCellNone) srec[atomicAdd(&cursor[c], 1u)] = __ldg(rec + 8 * i + k);
+      if (c != kCellNone) srec[atomicAdd(&cursor[c], 1u)] = ld_dep(rec + 8 * i + k);
     }
   }
 }
@@ -384,8 +384,8 @@ __device__ __forceinline__ void gather_cell(const Cell &c, const float *__restri
       const int z = c.iz + dz, y = c.iy + dy;
       const bool ok = (z < Vz) && (y < V);
       const float *row = g + ((size_t)(ok ? z : 0) * V + (ok ? y : 0)) * V;
-      G[dz][dy][0] = ok ? (double)__ldg(row + c.ix) : 0.0;
-      G[dz][dy][1] = (ok && c.ix + 1 < V) ? (double)__ldg(row + c.ix + 1) : 0.0;
+      G[dz][dy][0] = ok ? (double)ld_dep(row + c.ix) : 0.0;
+      G[dz][dy][1] = (ok && c.ix + 1 < V) ? (double)ld_dep(row + c.ix + 1) : 0.0;
     }
   const double wz[2] = {1.0 - c.rz, c.rz}, wy[2] = {1.0 - c.ry, c.ry}, wx[2] = {1.0 - c.rx, c.rx};
   gz = gy = gx = 0.0;
@@ -550,7 +550,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
       // SELECTED afterwards: an unwritten slot may hold anything, NaN included)
       const size_t idx = (size_t)b * a.N + n;
       const unsigned iz = cells.cellz[(size_t)b * cells.Npad + n];
-      const float4 s0 = __ldg(part + idx), s1 = __ldg(part + (size_t)a.P * a.N + idx);
+      const float4 s0 = ld_dep(part + idx), s1 = ld_dep(part + (size_t)a.P * a.N + idx);
       const bool in0 = iz != kCellNone, in1 = in0 && (int)iz + 1 < a.Vz;
       float gu0 = ((in0 ? s0.x : 0.f) + (in1 ? s1.x : 0.f)) * (float)(a.Vz - 1);
       float gu1 = ((in0 ? s0.y : 0.f) + (in1 ? s1.y : 0.f)) * (float)(a.V - 1);

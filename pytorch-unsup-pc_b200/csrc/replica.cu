@@ -131,7 +131,7 @@ select_points_kernel(const float *__restrict__ points, const int *__restrict__ s
                      int N_src, int M, int C, float *__restrict__ out) {
   const int b = blockIdx.y, m = blockIdx.x * 256 + threadIdx.x;
   if (m >= M) return;
-  const int src = __ldg(sel + (size_t)b * M + m);
+  const int src = min(max(__ldg(sel + (size_t)b * M + m), 0), N_src - 1);   // see point_offset()
   const float *p = points + ((size_t)(b / R) * N_src + src) * C;
   float *o = out + ((size_t)b * M + m) * C;
   for (int c = 0; c < C; ++c) o[c] = __ldg(p + c);
@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256)
 invert_selection_kernel(const int *__restrict__ sel, int N_src, int M, int *__restrict__ inv) {
   const int b = blockIdx.y, m = blockIdx.x * 256 + threadIdx.x;
   if (m >= M) return;
-  inv[(size_t)b * N_src + __ldg(sel + (size_t)b * M + m)] = m;
+  const int src = __ldg(sel + (size_t)b * M + m);
+  if ((unsigned)src < (unsigned)N_src) inv[(size_t)b * N_src + src] = m;   // never outside inv
 }
 
 // g_cloud[c][n][:] = sum_{r < R} g_rep[c R + r][slot(c R + r, n)][:]   (slot = n without dropout;

@@ -12,6 +12,7 @@ import torch
 from . import _lib
 
 _ws_cache = {}
+_retired = []        # superseded scratch buffers (see _scratch)
 
 
 def _ptr(t):
@@ -130,6 +131,11 @@ def _scratch(kind, nbytes, device):
     key = (kind, device.index, torch._C._cuda_getCurrentRawStream(device.index))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            # a CUDA graph captured over this path (pipeline.GraphedSteps) has the old pointer
+            # baked in: a superseded buffer is retired, never freed, so a replay can not write
+            # into memory the allocator has handed to another tensor
+            _retired.append(buf)
         buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf

@@ -94,6 +94,10 @@ class HostPipeline:
                     raise ValueError("%s: host tensors must be pinned for asynchronous copies" % name)
                 d = slot.get(name)
                 if d is None or d.shape != t.shape or d.dtype != t.dtype:
+                    if d is not None:
+                        # the replaced buffer was allocated on the copy stream but read by
+                        # kernels on the compute stream: tell the allocator before dropping it
+                        d.record_stream(cur)
                     d = torch.empty(t.shape, dtype=t.dtype, device=self.device)
                     slot[name] = d
                 d.copy_(t, non_blocking=True)

@@ -13,7 +13,10 @@ from . import _lib, ops
 # plane_local: build/gather every Z-plane in shared memory (default); False keeps
 # the raw grid in global memory (memset + atomic scatter, grid gather) -- same
 # results to rounding, kept for A/B measurements
-_options = {"voxels": True, "drc_probs": True, "deterministic": False, "plane_local": True}
+# validate_indices: range- and duplicate-check a user-supplied dropout selection (one small
+# reduction; one host sync when the selection lives on the device)
+_options = {"voxels": True, "drc_probs": True, "deterministic": False, "plane_local": True,
+            "validate_indices": True}
 
 
 def set_outputs(voxels=None, drc_probs=None):
@@ -155,8 +158,21 @@ def _selection(indices, P, N_src, device):
     if sel.dim() != 2 or sel.shape[0] != P or not 1 <= sel.shape[1] <= N_src:
         raise ValueError("indices must be [P,M] (or the reference's [P,M,2]) with P=%d and "
                          "1 <= M <= %d, got %s" % (P, N_src, tuple(sel.shape)))
-    if sel.is_floating_point():
+    if sel.is_floating_point() or sel.dtype == torch.bool:
         raise TypeError("indices must be an integer tensor")
+    if _options["validate_indices"]:
+        # an index outside the cloud would be an out-of-bounds access in the kernels, and a
+        # repeated one would keep a single slot of the backward's inverse map (the gradient of
+        # the other would be lost): refuse both.  The reference's sampler draws without
+        # replacement (point_cloud_to.py:279), so it never produces duplicates.
+        srt = torch.sort(sel.long(), dim=1).values
+        bad = torch.stack([srt[:, 0].min() < 0, srt[:, -1].max() >= N_src,
+                           (srt[:, 1:] == srt[:, :-1]).any()]).tolist()
+        if bad[0] or bad[1]:
+            raise ValueError("indices must lie in [0, %d)" % N_src)
+        if bad[2]:
+            raise ValueError("indices must be distinct within every row (sampling without "
+                             "replacement, point_cloud_to.py:279)")
     return sel.to(device=device, dtype=torch.int32).contiguous()
 
 

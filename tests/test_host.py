@@ -98,3 +98,23 @@ def test_anisotropic_kernel_lengths():
     cfg = default_cfg(vox_size=64, vox_size_z=32, pc_gauss_kernel_size=21)
     k = dpc.smoothing_kernel(cfg, 3.0)
     assert [tuple(t.shape) for t in k] == [(1, 1, 1, 1, 21), (1, 1, 1, 21, 1), (1, 1, 11, 1, 1)]
+
+
+def test_dropout_selection_is_validated():
+    """A user-supplied dropout selection is range- and duplicate-checked before any kernel sees
+    it (an out-of-range index would be an out-of-bounds access, a repeated one would lose a
+    gradient in the backward's inverse map)."""
+    from pytorch_unsup_pc_b200 import point_cloud as pc
+    ok = torch.tensor([[0, 3, 2], [1, 4, 0]])
+    assert pc._selection(ok, 2, 5, "cpu").dtype == torch.int32
+    pairs = torch.stack([torch.zeros_like(ok), ok], dim=-1)            # the reference's [P,M,2]
+    assert torch.equal(pc._selection(pairs, 2, 5, "cpu"), ok.int())
+    for bad in ([[0, 3, 5], [1, 4, 0]], [[0, -1, 2], [1, 4, 0]]):
+        with pytest.raises(ValueError, match="must lie in"):
+            pc._selection(torch.tensor(bad), 2, 5, "cpu")
+    with pytest.raises(ValueError, match="distinct"):
+        pc._selection(torch.tensor([[0, 3, 3], [1, 4, 0]]), 2, 5, "cpu")
+    with pytest.raises(TypeError):
+        pc._selection(torch.tensor([[0.0, 1.0, 2.0], [1.0, 4.0, 0.0]]), 2, 5, "cpu")
+    with pc.options(validate_indices=False):
+        pc._selection(torch.tensor([[0, 3, 3], [1, 4, 0]]), 2, 5, "cpu")

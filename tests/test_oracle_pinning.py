@@ -88,3 +88,39 @@ def test_oracle_matches_live_reference():
                      CF.smoothing_taps(cfg, 1.2), case["scale"], case["focal"])
     for k in ("proj", "proj_depth", "tr_pc", "voxels", "drc_probs", "voxels_raw"):
         assert torch.equal(ref[k], orc[k]), k
+
+
+MIRRORED = {
+    "pc_to": ["pointcloud_project_fast", "pc_perspective_transform", "pointcloud2voxels3d_fast",
+              "smoothen_voxels3d", "convolve_rgb", "pc_point_dropout"],
+    "drc": ["drc_projection", "drc_depth_projection", "drc_event_probabilities",
+            "project_volume_rgb_integral"],
+    "gauss_kernel": ["smoothing_kernel", "gauss_kernel_1d", "separable_kernels"],
+}
+
+
+@pytest.mark.skipif(not RL.available(), reason="reference tree not mounted")
+def test_mirror_signatures_match_live_reference():
+    """The drop-in claim, guarded: every mirrored function takes the reference's parameters, by
+    the same names, in the same order, with the same defaults.  A mirror may APPEND optional
+    parameters (pc_point_dropout's seed / indices); it may not rename, reorder or drop any."""
+    import inspect
+    import sys
+    import pytorch_unsup_pc_b200 as dpc
+    mods = RL.load()
+    if RL._DPC not in sys.path:
+        sys.path.insert(0, RL._DPC)
+    import util.point_cloud_distance as pcd
+    mods = dict(mods, pcd=pcd)
+    names = dict(MIRRORED, pcd=["point_cloud_distance"])
+    for mod, fns in names.items():
+        for fn in fns:
+            ref = list(inspect.signature(getattr(mods[mod], fn)).parameters.values())
+            mine = list(inspect.signature(getattr(dpc, fn)).parameters.values())
+            assert len(mine) >= len(ref), fn
+            for r, m in zip(ref, mine):
+                assert (r.name, r.kind) == (m.name, m.kind), (fn, r, m)
+                assert r.default == m.default or (r.default is inspect.Parameter.empty
+                                                  and m.default is inspect.Parameter.empty), (fn, r, m)
+            for extra in mine[len(ref):]:
+                assert extra.default is not inspect.Parameter.empty, (fn, extra)
