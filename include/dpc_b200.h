@@ -245,6 +245,68 @@ DPC_API int dpc_project_replicated_bwd(const dpc_params *p, int replicas, int N_
                     float *g_points, float *g_quat, float *g_trans,
                     float *g_focal, float *g_scale,
                     void *workspace, size_t workspace_bytes, void *stream);
+/* ---- the renderer and its loss as ONE step (f2 -> the path -> f1) ------------
+ * Reference: ModelPointCloud.forward models/model_pc_to.py:302-331 (tf_repeat_0
+ * of clouds and scales over views x candidates, pc_point_dropout,
+ * pointcloud_project_fast) followed by add_proj_loss :339-385 and
+ * proj_loss_pose_candidates :410-440, and the autograd of all of it.
+ *
+ * P = BV * num_candidates projections, BV = clouds * views, replicas = views *
+ * num_candidates (candidates of a view adjacent, views of a cloud adjacent:
+ * tf_repeat_0 order).  points / sel / pose inputs as in
+ * dpc_project_replicated_fwd; gt [BV,G,G], weights [BV] (NULL ok), as in
+ * dpc_candidate_loss_fwd; p->outputs must be 0.
+ * Forward outputs: mask [P,V,V] (the candidate masks), all_loss [BV*C],
+ * min_idx [BV], view_loss [BV], loss [1] = weight_scale / BV * sum(view_loss),
+ * winners [BV] int32 (projection index of every view's winning candidate) and
+ * kcoef [BV] (factor of its mask gradient) -- both state for the backward, as
+ * are grid_b / clamp_bits / cells. */
+DPC_API int dpc_render_loss_fwd(const dpc_params *p, int replicas, int N_src,
+                    const int32_t *sel /*NULL ok*/,
+                    const float *points, const float *quat,
+                    const float *trans /*NULL ok*/, const float *focal /*NULL ok*/,
+                    const float *scale /*NULL ok*/,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz, int scatter_mode,
+                    int num_candidates, int G, const float *gt, const float *weights /*NULL ok*/,
+                    float weight_scale,
+                    float *grid_b, uint32_t *clamp_bits, void *cells /*NULL ok*/, float *mask,
+                    float *all_loss, int64_t *min_idx, float *view_loss, float *loss,
+                    int32_t *winners, float *kcoef,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* Backward of the step: g_points [P/replicas, N_src, 3] (summed over views and
+ * candidates), g_quat [P,4], g_trans [P,3], g_focal [P], g_scale [P] (each
+ * NULL when its input is) times the device scalar `upstream` (NULL = 1).
+ * The one-hot candidate mask (model_pc_to.py:425-430) makes the gradient of
+ * every losing candidate exactly zero: when the forward saved the fast ray
+ * state (cells given, atomic scatter, cubic grid, log-sum DRC) the backward
+ * chain runs over the BV winners only and dL/dmask is built inside the ray
+ * kernel; otherwise it is written to g_mask_scratch [P,V,V] and the general
+ * backward runs.  scatter_mode: the forward's.
+ * Scratch, in projection SLOTS = dpc_render_loss_slots() (BV or P):
+ * g_grid [slots,Vz,V,V], g_points_rep [slots,N,3], inv_scratch [slots,N_src]
+ * int32 (needed when sel != NULL). */
+DPC_API int dpc_render_loss_bwd(const dpc_params *p, int replicas, int N_src,
+                    const int32_t *sel /*NULL ok*/,
+                    const float *points, const float *quat,
+                    const float *trans, const float *focal, const float *scale,
+                    const float *taps_x_host, int kx, const float *taps_y_host, int ky,
+                    const float *taps_z_host, int kz, int scatter_mode,
+                    int num_candidates, int G, const float *gt, const float *weights /*NULL ok*/,
+                    float weight_scale,
+                    const float *grid_b, const uint32_t *clamp_bits, const void *cells /*NULL ok*/,
+                    const float *mask, const int64_t *min_idx, const int32_t *winners,
+                    const float *kcoef, const float *upstream /*NULL ok*/,
+                    float *g_grid, float *g_points_rep, int32_t *inv_scratch /*NULL ok*/,
+                    float *g_mask_scratch /*NULL ok when slots == BV*/,
+                    float *g_points, float *g_quat, float *g_trans,
+                    float *g_focal, float *g_scale,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* Projection slots the backward's scratch must hold: BV when the winner-only
+ * chain applies to this geometry / mode, else P (host-side query). */
+DPC_API int dpc_render_loss_slots(const dpc_params *p, int num_candidates, int have_cells,
+                          int scatter_mode);
+
 /* The sampler of pc_point_dropout (point_cloud_to.py:275-283) on the device:
  * sel [P,M] = a uniformly random M-subset of [0, N_src) per projection, in
  * ascending order, a pure function of (seed, projection index).  Same

@@ -15,14 +15,14 @@ from .point_cloud import (pc_perspective_transform, pointcloud2voxels3d_fast,
 from .drc import (drc_depth_projection, drc_event_probabilities, drc_projection,
                   project_volume_rgb_integral)
 from .pipeline import AlternatingGraphs, GraphedSteps, HostPipeline, bind_to_device_numa
-from .losses import add_proj_loss, proj_loss_pose_candidates
+from .losses import add_proj_loss, proj_loss_pose_candidates, project_candidates_loss
 from .point_cloud_distance import chamfer_distances, point_cloud_distance
 
 __all__ = [
     "pointcloud_project_fast", "pc_perspective_transform", "pointcloud2voxels3d_fast",
     "smoothen_voxels3d", "drc_projection", "drc_depth_projection", "drc_event_probabilities",
     "smoothing_kernel", "gauss_kernel_1d", "separable_kernels",
-    "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "AlternatingGraphs", "bind_to_device_numa", "add_proj_loss", "proj_loss_pose_candidates", "point_cloud_distance", "chamfer_distances",
+    "set_outputs", "set_deterministic", "options", "HostPipeline", "GraphedSteps", "AlternatingGraphs", "bind_to_device_numa", "add_proj_loss", "proj_loss_pose_candidates", "project_candidates_loss", "point_cloud_distance", "chamfer_distances",
     "pc_point_dropout", "pointcloud_project_replicated", "convolve_rgb",
     "project_volume_rgb_integral",
     "library_path", "version", "Config", "default_cfg",

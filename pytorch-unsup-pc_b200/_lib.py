@@ -80,6 +80,16 @@ SIGNATURES = {
                        c_void_p, c_void_p, c_void_p],
     "dpc_candidate_loss_fwd": [c_int] * 4 + [c_void_p] * 6 + [c_void_p],
     "dpc_candidate_loss_bwd": [c_int] * 4 + [c_void_p] * 5 + [ctypes.c_float, c_void_p, c_void_p],
+    "dpc_render_loss_fwd": [_P, c_int, c_int, c_void_p] + [c_void_p] * 5
+                       + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
+                       + [c_int, c_int, c_void_p, c_void_p, ctypes.c_float]
+                       + [c_void_p] * 4 + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p],
+    "dpc_render_loss_bwd": [_P, c_int, c_int, c_void_p] + [c_void_p] * 5
+                       + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]
+                       + [c_int, c_int, c_void_p, c_void_p, ctypes.c_float]
+                       + [c_void_p] * 8 + [c_void_p] * 4 + [c_void_p] * 5
+                       + [c_void_p, c_size_t, c_void_p],
+    "dpc_render_loss_slots": [_P, c_int, c_int, c_int],
     "dpc_point_cloud_distance": [c_int, c_int] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p],
     "dpc_project_profile": [_P] + [c_void_p] * 5
                            + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int]

@@ -408,6 +408,23 @@ struct FwdPtrs {
   Replica rep;
 };
 
+// Projections [b0, ...) of a batch: the cloud tensor and the selection rows they start at.  A
+// replica-aware range starts at a multiple of `replicas` (replica_chunk), so that projection
+// b0 + i of the batch is replica i % replicas of cloud b0 / replicas + i / replicas.
+static const float *range_points(const float *points, const Replica &rep, int b0, int N) {
+  if (rep.replicas == 0) return points + (size_t)b0 * N * 3;
+  return points + (size_t)(b0 / rep.replicas) * rep.N_src * 3;
+}
+static Replica range_replica(const Replica &rep, int b0, int N) {
+  Replica r = rep;
+  if (r.sel) r.sel += (size_t)b0 * N;
+  return r;
+}
+static int replica_chunk(const dpc_params *p, const Replica &rep) {
+  const int c = chunk_size(p);
+  return (rep.replicas > 0 && c % rep.replicas != 0) ? p->P : c;
+}
+
 // The plane-local path packs (n, iy, ix) into 32 bits and bins by a z-cell byte.
 static bool plane_local_ok(const dpc_params *p) {
   return p->N <= 65535 && p->V <= 256 && p->Vz <= 192;
@@ -442,10 +459,9 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   dpc_params sp = *p;
   sp.P = n;
   const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V, I = (size_t)p->V * p->V;
-  // (a replica-aware pass always covers the whole batch: b0 == 0)
-  const PoseArgs pa = pose_args(&sp, q.points + b0 * N3, q.quat + b0 * 4,
+  const PoseArgs pa = pose_args(&sp, range_points(q.points, q.rep, b0, p->N), q.quat + b0 * 4,
                                 q.trans ? q.trans + b0 * 3 : nullptr,
-                                q.focal ? q.focal + b0 : nullptr, q.rep);
+                                q.focal ? q.focal + b0 : nullptr, range_replica(q.rep, b0, p->N));
   float *grid = q.grid_b + b0 * G;
   float *tr_pc = q.tr_pc ? q.tr_pc + b0 * N3 : nullptr;
   stage_mark(s);
@@ -516,7 +532,7 @@ static int project_fwd_impl(const dpc_params *p, const Replica &rep, const float
   cudaStream_t s = (cudaStream_t)stream;
   const FwdPtrs q{points, quat, trans, focal, scale, tr_pc, grid_b, clamp_bits, mask, depth, voxels,
                   probs, cells, rep};
-  const int chunk = rep.replicas > 0 ? p->P : chunk_size(p);
+  const int chunk = replica_chunk(p, rep);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   if (!pl) return project_fwd_range(p, 0, p->P, q, tx, kx, ty, ky, tz, kz, scatter_mode, w, s);
   cudaEventRecord(pl->fork, s);
@@ -575,9 +591,9 @@ static int project_bwd_range(const dpc_params *p, int b0, int n, const BwdPtrs &
   dpc_params sp = *p;
   sp.P = n;
   const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V, I = (size_t)p->V * p->V;
-  const PoseArgs pa = pose_args(&sp, q.points + b0 * N3, q.quat + b0 * 4,
+  const PoseArgs pa = pose_args(&sp, range_points(q.points, q.rep, b0, p->N), q.quat + b0 * 4,
                                 q.trans ? q.trans + b0 * 3 : nullptr,
-                                q.focal ? q.focal + b0 : nullptr, q.rep);
+                                q.focal ? q.focal + b0 : nullptr, range_replica(q.rep, b0, p->N));
   float *g_grid = q.g_grid + b0 * G;
   DrcArgs da = drc_args(&sp, q.grid_b + b0 * G, q.scale ? q.scale + b0 : nullptr);
   da.P_total = p->P;
@@ -667,7 +683,7 @@ static int project_bwd_impl(const dpc_params *p, const Replica &rep, const float
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, g_mask, g_depth, g_probs,
                   g_voxels, g_tr_pc, g_grid, g_points, g_quat, g_trans, g_focal, g_scale,
                   const_cast<void *>(cells), rep, fast_rays};
-  const int chunk = rep.replicas > 0 ? p->P : chunk_size(p);
+  const int chunk = replica_chunk(p, rep);
   Pipeline *pl = chunk < p->P ? get_pipeline() : nullptr;
   int rc = DPC_OK;
   if (!pl) {
@@ -791,6 +807,183 @@ int dpc_candidate_loss_bwd(int BV, int C, int V, int G, const float *gt, const f
   DPC_REQUIRE(gt); DPC_REQUIRE(pred); DPC_REQUIRE(min_idx); DPC_REQUIRE(g_pred);
   return launch_candidate_loss_bwd(gt, pred, weights, (const long long *)min_idx, upstream, coeff,
                                    BV, C, V, G, g_pred, (cudaStream_t)stream);
+}
+
+// ---- fused renderer + candidate-selection loss (f2 -> the path -> f1) -----------
+// models/model_pc_to.py:302-331 (replication, dropout, projection) + :339-385, 410-440 (loss).
+// The gradient of the loss reaches the projection of the WINNING candidate of every view only
+// (one-hot mask, :425-430); the losing candidates' gradients are exactly zero.  When the forward
+// saved the fast ray state the backward chain therefore runs over the BV winners (chain slots,
+// bmap = winners) and the ray kernel builds dL/dmask on the fly; otherwise dL/dmask is written
+// out for all P projections and the general backward runs.
+static bool render_winner_only(const dpc_params *p, const void *cells, int scatter_mode) {
+  return plane_local_ok(p) && fast_ray_state(p, cells, scatter_mode);
+}
+
+static int check_render_args(const dpc_params *p, int replicas, int C, int G) {
+  if (C < 1 || replicas % C != 0) {
+    set_error("render_loss: replicas=%d must be views x num_candidates=%d", replicas, C);
+    return DPC_ERR_ARG;
+  }
+  if (p->outputs != 0) {
+    set_error("render_loss: params.outputs must be 0 (no voxels / probs)");
+    return DPC_ERR_ARG;
+  }
+  return check_loss_args(p->P / C, C, p->V, G);
+}
+
+int dpc_render_loss_slots(const dpc_params *p, int num_candidates, int have_cells, int scatter_mode) {
+  if (!p || p->P < 1 || num_candidates < 1 || p->P % num_candidates) return 0;
+  return render_winner_only(p, have_cells ? (const void *)p : nullptr, scatter_mode)
+             ? p->P / num_candidates : p->P;
+}
+
+int dpc_render_loss_fwd(const dpc_params *p, int replicas, int N_src, const int32_t *sel,
+                        const float *points, const float *quat, const float *trans,
+                        const float *focal, const float *scale, const float *tx, int kx,
+                        const float *ty, int ky, const float *tz, int kz, int scatter_mode,
+                        int num_candidates, int G, const float *gt, const float *weights,
+                        float weight_scale, float *grid_b, uint32_t *clamp_bits, void *cells,
+                        float *mask, float *all_loss, int64_t *min_idx, float *view_loss,
+                        float *loss, int32_t *winners, float *kcoef, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+  DPC_TRY(check_params(p, true));
+  DPC_TRY(check_replica(p, replicas, N_src, sel));
+  DPC_TRY(check_render_args(p, replicas, num_candidates, G));
+  DPC_REQUIRE(gt); DPC_REQUIRE(all_loss); DPC_REQUIRE(min_idx); DPC_REQUIRE(view_loss);
+  DPC_REQUIRE(loss); DPC_REQUIRE(winners); DPC_REQUIRE(kcoef);
+  Replica rep;
+  rep.replicas = replicas; rep.N_src = N_src; rep.sel = sel;
+  DPC_TRY(project_fwd_impl(p, rep, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz,
+                           scatter_mode, nullptr, grid_b, clamp_bits, cells, mask, nullptr, nullptr,
+                           nullptr, workspace, workspace_bytes, stream));
+  const int BV = p->P / num_candidates;
+  const float coeff = weight_scale / (float)BV;
+  cudaStream_t s = (cudaStream_t)stream;
+  DPC_TRY(launch_candidate_loss_fwd(gt, mask, weights, BV, num_candidates, p->V, G, all_loss,
+                                    (long long *)min_idx, view_loss, s, winners, kcoef, coeff));
+  return launch_loss_total(view_loss, BV, coeff, loss, s);
+}
+
+// chain slots [j0, j0 + n) of the winner-only backward on stream s
+static int render_bwd_range(const dpc_params *p, int j0, int n, const BwdPtrs &q, const LossGrad &lg0,
+                            const float *tx, int kx, const float *ty, int ky, const float *tz,
+                            int kz, const Workspace &w, cudaStream_t s) {
+  dpc_params sp = *p;
+  sp.P = n;                                        // slots of this range
+  const size_t N3 = (size_t)p->N * 3, G = (size_t)p->Vz * p->V * p->V;
+  const int spb = drc_scale_partial_blocks(p->V), ppb = pose_partial_blocks(p->N);
+  LossGrad lg = lg0;
+  lg.bmap += j0;
+  // everything that belongs to a projection (inputs, saved state, pose gradients) is passed
+  // whole-batch and addressed through bmap; everything that belongs to a slot is offset here
+  PoseArgs pa = pose_args(&sp, q.points, q.quat, q.trans, q.focal, q.rep);
+  pa.bmap = lg.bmap;
+  float *g_grid = q.g_grid + j0 * G;
+  DrcArgs da = drc_args(&sp, q.grid_b, q.scale);
+  da.P_total = p->P;
+  set_ray_state(da, p, q.fast_rays, 0);
+  stage_mark(s);
+  DPC_TRY(launch_drc_blurz_bwd(da, tz, kz, nullptr, nullptr, nullptr, nullptr, g_grid,
+                               w.scale_partials + (size_t)j0 * spb, w.counters + j0, n, s, &lg));
+  stage_mark(s);
+  BlurXYArgs b;
+  b.src = g_grid; b.dst = g_grid; b.bits_out = nullptr; b.bits_in = q.bits;
+  b.planes = n * p->Vz; b.V = p->V; b.clamp_in = false;
+  float rx[DPC_MAX_TAPS], ry[DPC_MAX_TAPS];
+  for (int i = 0; i < kx; ++i) rx[i] = tx[kx - 1 - i];
+  for (int i = 0; i < ky; ++i) ry[i] = ty[ky - 1 - i];
+  b.cells = cells_view(q.cells, p->P, p->N, p->Vz);
+  float4 *part = w.part + (size_t)2 * j0 * p->N;
+  b.part = part; b.Vz = p->Vz; b.N = p->N; b.P = n; b.bmap = lg.bmap;
+  DPC_TRY(launch_blur_xy(b, rx, kx, ry, ky, s));
+  stage_mark(s);
+  DPC_TRY(launch_pose_bwd_partials(
+      pa, b.cells, part, nullptr, q.g_points + j0 * N3, w.pose_partials + (size_t)j0 * ppb * 8,
+      w.counters + j0, q.scale ? w.scale_partials + (size_t)j0 * spb : nullptr, spb, q.g_quat,
+      (q.trans && q.g_trans) ? q.g_trans : nullptr, (q.focal && q.g_focal) ? q.g_focal : nullptr,
+      (q.scale && q.g_scale) ? q.g_scale : nullptr, s));
+  stage_mark(s);
+  return DPC_OK;
+}
+
+int dpc_render_loss_bwd(const dpc_params *p, int replicas, int N_src, const int32_t *sel,
+                        const float *points, const float *quat, const float *trans,
+                        const float *focal, const float *scale, const float *tx, int kx,
+                        const float *ty, int ky, const float *tz, int kz, int scatter_mode,
+                        int num_candidates, int G, const float *gt, const float *weights,
+                        float weight_scale, const float *grid_b, const uint32_t *clamp_bits,
+                        const void *cells, const float *mask, const int64_t *min_idx,
+                        const int32_t *winners, const float *kcoef, const float *upstream,
+                        float *g_grid, float *g_points_rep, int32_t *inv_scratch,
+                        float *g_mask_scratch, float *g_points, float *g_quat, float *g_trans,
+                        float *g_focal, float *g_scale, void *workspace, size_t workspace_bytes,
+                        void *stream) {
+  DPC_TRY(check_params(p, true));
+  DPC_TRY(check_replica(p, replicas, N_src, sel));
+  DPC_TRY(check_render_args(p, replicas, num_candidates, G));
+  DPC_REQUIRE(points); DPC_REQUIRE(quat); DPC_REQUIRE(grid_b); DPC_REQUIRE(clamp_bits);
+  DPC_REQUIRE(gt); DPC_REQUIRE(mask); DPC_REQUIRE(min_idx); DPC_REQUIRE(winners); DPC_REQUIRE(kcoef);
+  DPC_REQUIRE(g_grid); DPC_REQUIRE(g_points_rep); DPC_REQUIRE(g_points); DPC_REQUIRE(g_quat);
+  if (sel) DPC_REQUIRE(inv_scratch);
+  const int C = num_candidates, BV = p->P / C;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (scatter_mode == DPC_SCATTER_SORTED) cells = nullptr;
+  if (!render_winner_only(p, cells, scatter_mode)) {
+    // general saved state: dL/dmask for all P projections (zeros for the losers), then the
+    // replica-aware backward
+    DPC_REQUIRE(g_mask_scratch);
+    DPC_TRY(launch_candidate_loss_bwd(gt, mask, weights, (const long long *)min_idx, upstream,
+                                      weight_scale / (float)BV, BV, C, p->V, G, g_mask_scratch, s));
+    return dpc_project_replicated_bwd(p, replicas, N_src, sel, points, quat, trans, focal, scale,
+                                      tx, kx, ty, ky, tz, kz, grid_b, clamp_bits, cells,
+                                      g_mask_scratch, nullptr, nullptr, nullptr, nullptr, g_grid,
+                                      g_points_rep, inv_scratch, g_points, g_quat, g_trans, g_focal,
+                                      g_scale, workspace, workspace_bytes, stream);
+  }
+  DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
+  DPC_TRY(check_taps(tz, kz, "taps_z"));
+  DPC_TRY(check_ws(p, workspace, workspace_bytes));
+  const Workspace w = carve(p, workspace);
+  // pose gradients of the losing candidates: exactly zero
+  bool ok = cudaMemsetAsync(g_quat, 0, (size_t)p->P * 4 * sizeof(float), s) == cudaSuccess;
+  if (trans && g_trans) ok = ok && cudaMemsetAsync(g_trans, 0, (size_t)p->P * 3 * sizeof(float), s) == cudaSuccess;
+  if (focal && g_focal) ok = ok && cudaMemsetAsync(g_focal, 0, (size_t)p->P * sizeof(float), s) == cudaSuccess;
+  if (scale && g_scale) ok = ok && cudaMemsetAsync(g_scale, 0, (size_t)p->P * sizeof(float), s) == cudaSuccess;
+  if (!ok) return check_launch("render_loss_bwd: memset");
+  Replica rep;
+  rep.replicas = replicas; rep.N_src = N_src; rep.sel = sel;
+  LossGrad lg;
+  lg.bmap = winners; lg.gt = gt; lg.pred = mask; lg.kcoef = kcoef; lg.upstream = upstream;
+  lg.G = G; lg.C = C;
+  const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, nullptr, nullptr, nullptr,
+                  nullptr, nullptr, g_grid, g_points_rep, g_quat, g_trans, g_focal, g_scale,
+                  const_cast<void *>(cells), rep, const_cast<void *>(cells)};
+  // the winners as two half-chains on the two internal streams from 64 slots on (as the batch is)
+  dpc_params slots = *p;
+  slots.P = BV;
+  const int chunk = chunk_size(&slots);
+  Pipeline *pl = chunk < BV ? get_pipeline() : nullptr;
+  int rc = DPC_OK;
+  if (!pl) {
+    rc = render_bwd_range(p, 0, BV, q, lg, tx, kx, ty, ky, tz, kz, w, s);
+  } else {
+    cudaEventRecord(pl->fork, s);
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(pl->side[i], pl->fork, 0);
+    for (int j0 = 0, c = 0; j0 < BV && rc == DPC_OK; j0 += chunk, ++c) {
+      const int n = BV - j0 < chunk ? BV - j0 : chunk;
+      rc = render_bwd_range(p, j0, n, q, lg, tx, kx, ty, ky, tz, kz, w, pl->side[c & 1]);
+    }
+    for (int i = 0; i < 2; ++i) {
+      cudaEventRecord(pl->join[i], pl->side[i]);
+      cudaStreamWaitEvent(s, pl->join[i], 0);
+    }
+  }
+  DPC_TRY(rc);
+  // cloud gradient = sum over the views of a cloud of its winners' point gradients, routed
+  // through their dropout selections (autograd of tf_repeat_0 and of the gather)
+  return launch_replica_reduce(g_points_rep, sel, inv_scratch, BV, replicas / C, N_src, p->N, 3,
+                               g_points, s, winners);
 }
 
 // ---- f4: nearest neighbour of the Chamfer evaluation ---------------------------

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(XYCfg<V, R>::THREADS, XYCfg<V, R>::MINB)
 blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                uint32_t *__restrict__ bits_out, const uint32_t *__restrict__ bits_in,
                const Taps<R> kx, const Taps<R> ky, const CellsView cells,
-               float4 *__restrict__ part, int Vz, int N, int P) {
+               float4 *__restrict__ part, int Vz, int N, int P, const int *__restrict__ bmap) {
   using C = XYCfg<V, R>;
   static_assert(!POINTS || (WRITE_BITS != MASK_OUT), "POINTS: forward (bits out) or backward (mask)");
   constexpr int HALF = C::RH / 2;
@@ -287,7 +287,11 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 
   // the points touching this plane: the range now, the thread's first record right behind it --
   // both are in flight while the tile is zeroed (forward) / filled and blurred (backward)
-  const int pb = POINTS ? (int)(plane / Vz) : 0, pz = POINTS ? (int)(plane - (size_t)pb * Vz) : 0;
+  // (winner-only backward: the launch covers chain slots; slot pj holds the gradient planes of
+  // projection pb = bmap[pj] -- src / part are indexed by the slot, bits_in / cells by pb)
+  const int pj = POINTS ? (int)(plane / Vz) : 0, pz = POINTS ? (int)(plane - (size_t)pj * Vz) : 0;
+  const int pb = (POINTS && MASK_OUT && bmap) ? __ldg(bmap + pj) : pj;
+  const size_t bplane = POINTS ? (size_t)pb * Vz + pz : plane;      // plane index of the clamp bits
   TouchRange touch = {0u, 0u, 0u, nullptr};
   uint4 rec0 = make_uint4(0u, 0u, 0u, 0u);
   if (POINTS && DPC_XY_PREFETCH) {
@@ -318,7 +322,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #pragma unroll
     for (int i = 0; i < MW; ++i)
       mword[i] = tid + i * C::THREADS < MWORDS
-                     ? __ldg(bits_in + plane * MWORDS + tid + i * C::THREADS) : 0u;
+                     ? __ldg(bits_in + bplane * MWORDS + tid + i * C::THREADS) : 0u;
   }
   // (pads only: measured 498 -> 484 us at 128^2, but 43.0 -> 46.7 us at 64^2, where the whole
   // tile is 11 vector stores per thread)
@@ -485,7 +489,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
     // DPC_XY_SPARSE_Q / 4 per thread) take the dense pass below.
     const uint32_t n_touch = touch.hi - touch.lo;
     if (4 * n_touch <= (uint32_t)(DPC_XY_SPARSE_Q * C::THREADS)) {
-      const uint32_t *mb = bits_in + plane * (V * V / 32);
+      const uint32_t *mb = bits_in + bplane * (V * V / 32);
       for_each_touching_point(touch, tid, C::THREADS, rec0, [&](const uint4 r, int dz) {
         const int n = (int)(r.x >> 16), iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
         const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
@@ -523,7 +527,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
         const float sz = wy0 * (wx0 * G00 + rx * G01) + ry * (wx0 * G10 + rx * G11);
         const float sy = wz * (wx0 * (G10 - G00) + rx * (G11 - G01));
         const float sx = wz * (wy0 * (G01 - G00) + ry * (G11 - G10));
-        part[((size_t)dz * P + pb) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
+        part[((size_t)dz * P + pj) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
       });
       return;
     }
@@ -541,7 +545,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #ifndef DPC_PROBE_NO_MASK
       if (MASK_OUT) {
         const uint32_t wbits = BITS_SMEM ? mask_s[((y0 + j) * V + 2 * cp) / 32]
-                                         : __ldg(bits_in + plane * MWORDS + ((y0 + j) * V + 2 * cp) / 32);
+                                         : __ldg(bits_in + bplane * MWORDS + ((y0 + j) * V + 2 * cp) / 32);
         const uint32_t sh = (2 * cp) & 31;
         lo = ((wbits >> sh) & 1u) ? lo : 0.f;
         hi = ((wbits >> (sh + 1)) & 1u) ? hi : 0.f;
@@ -568,7 +572,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       const float sz = wy0 * (wx0 * G00 + rx * G01) + ry * (wx0 * G10 + rx * G11);
       const float sy = wz * (wx0 * (G10 - G00) + rx * (G11 - G01));
       const float sx = wz * (wy0 * (G01 - G00) + ry * (G11 - G10));
-      part[((size_t)dz * P + pb) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
+      part[((size_t)dz * P + pj) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
     });
   }
 #endif
@@ -591,7 +595,7 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     }                                                                                          \
     launch_dep(blur_xy_kernel<V, R, CL, WB, MO, PT>, g, t, smem, s, a.src, a.dst, a.bits_out,  \
-               a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P);                            \
+               a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P, a.bmap);                    \
   } while (0)
   const bool points = a.cells.cellz != nullptr;
   if (points && (a.Vz < 1 || a.N < 1 || a.P < 1 || (!a.bits_in && !a.bits_out) ||

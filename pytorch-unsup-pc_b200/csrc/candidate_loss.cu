@@ -21,27 +21,12 @@ namespace dpc {
 constexpr int kLossThreads = 256;
 constexpr int kMaxCandidates = 16;
 
-// average of the n x n block of gt that pools onto pixel (y, x) (AvgPool2d(n))
-__device__ __forceinline__ float pooled_gt(const float *__restrict__ gt, int G, int n, int y, int x) {
-  if (n == 1) return __ldg(gt + y * G + x);
-  float s = 0.f;
-  for (int dy = 0; dy < n; ++dy) {
-    const float *row = gt + (size_t)(y * n + dy) * G + x * n;
-    if (n == 2) {
-      const float2 v = __ldg(reinterpret_cast<const float2 *>(row));
-      s += v.x + v.y;
-    } else {
-      for (int dx = 0; dx < n; ++dx) s += __ldg(row + dx);
-    }
-  }
-  return s / (float)(n * n);
-}
-
 __global__ void __launch_bounds__(kLossThreads)
 candidate_loss_fwd_kernel(const float *__restrict__ gt, const float *__restrict__ pred,
                           const float *__restrict__ weights, int C, int V, int G,
                           float *__restrict__ all_loss, long long *__restrict__ min_idx,
-                          float *__restrict__ view_loss) {
+                          float *__restrict__ view_loss, int *__restrict__ winners,
+                          float *__restrict__ kcoef, float coeff) {
   const int bv = blockIdx.x, tid = threadIdx.x, n = G / V, VV = V * V;
   const float *g = gt + (size_t)bv * G * G;
   float acc[kMaxCandidates];
@@ -80,6 +65,13 @@ candidate_loss_fwd_kernel(const float *__restrict__ gt, const float *__restrict_
     const double w = weights ? (double)weights[bv] : 1.0;
     min_idx[bv] = arg;
     view_loss[bv] = (float)(w * w * best);
+    // render_loss: the winning projection of the view and the factor of its mask gradient,
+    // rounded exactly as candidate_loss_bwd_kernel rounds it
+    if (winners) winners[bv] = bv * C + arg;
+    if (kcoef) {
+      const float wf = weights ? weights[bv] : 1.f;
+      kcoef[bv] = -2.f * wf * wf * coeff;
+    }
   }
 }
 
@@ -107,10 +99,26 @@ candidate_loss_bwd_kernel(const float *__restrict__ gt, const float *__restrict_
 
 int launch_candidate_loss_fwd(const float *gt, const float *pred, const float *weights, int BV,
                               int C, int V, int G, float *all_loss, long long *min_idx,
-                              float *view_loss, cudaStream_t s) {
+                              float *view_loss, cudaStream_t s, int *winners, float *kcoef,
+                              float coeff) {
   candidate_loss_fwd_kernel<<<BV, kLossThreads, 0, s>>>(gt, pred, weights, C, V, G, all_loss,
-                                                           min_idx, view_loss);
+                                                           min_idx, view_loss, winners, kcoef, coeff);
   return check_launch("candidate_loss_fwd");
+}
+
+// loss = coeff * sum_bv view_loss[bv]: one warp, lanes stride over the views, fixed shuffle tree
+__global__ void loss_total_kernel(const float *__restrict__ view_loss, int BV, float coeff,
+                                  float *__restrict__ loss) {
+  double v = 0;
+  for (int i = threadIdx.x; i < BV; i += 32) v += (double)view_loss[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (threadIdx.x == 0) loss[0] = (float)(v * (double)coeff);
+}
+
+int launch_loss_total(const float *view_loss, int BV, float coeff, float *loss, cudaStream_t s) {
+  loss_total_kernel<<<1, 32, 0, s>>>(view_loss, BV, coeff, loss);
+  return check_launch("loss_total");
 }
 
 int launch_candidate_loss_bwd(const float *gt, const float *pred, const float *weights,

@@ -123,6 +123,10 @@ struct PoseArgs {
   // [P,N,3] as the reference holds it.
   const int *sel = nullptr;
   int replicas = 0, N_src = 0;
+  // Winner-only backward (render_loss): the chain runs over P slots; slot j works on the real
+  // projection bmap[j] (inputs, saved state, pose-gradient outputs) and keeps its scratch and
+  // its per-point gradients at slot j.  NULL: slot == projection.
+  const int *bmap = nullptr;
 };
 #ifdef __CUDACC__
 // float offset of point n of projection b in a.points
@@ -219,6 +223,37 @@ int launch_finalize(const PoseArgs &a, const double *pose_partials, int pose_blo
                     const float *scale_partials, int scale_blocks, float *g_quat, float *g_trans,
                     float *g_focal, float *g_scale, cudaStream_t s);
 
+// Fused renderer + candidate-selection loss (render_loss; models/model_pc_to.py:339-385,
+// 410-440): the backward ray kernel builds dL/dmask on the fly,
+//   dL/dmask[b] = kcoef[bv] * upstream * (pool(gt[bv]) - pred[b])      for the winning candidate,
+// and the backward chain runs over the winners only (bmap, see PoseArgs) -- the losing
+// candidates' gradients are exactly zero.
+struct LossGrad {
+  const int *bmap = nullptr;        // [slots] real projection of every chain slot (NULL: identity)
+  const float *gt = nullptr;        // [BV][G][G] ground-truth masks (NULL: plain g_mask is used)
+  const float *pred = nullptr;      // [P][V][V] the forward's masks
+  const float *kcoef = nullptr;     // [BV] -2 w^2 weight_scale / BV per view
+  const float *upstream = nullptr;  // device scalar dL/dloss, or NULL (= 1)
+  int G = 0, C = 1;
+};
+#ifdef __CUDACC__
+// average of the n x n block of gt that pools onto pixel (y, x) (AvgPool2d(n), model_pc_to.py:349-356)
+__device__ __forceinline__ float pooled_gt(const float *__restrict__ gt, int G, int n, int y, int x) {
+  if (n == 1) return __ldg(gt + y * G + x);
+  float s = 0.f;
+  for (int dy = 0; dy < n; ++dy) {
+    const float *row = gt + (size_t)(y * n + dy) * G + x * n;
+    if (n == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2 *>(row));
+      s += v.x + v.y;
+    } else {
+      for (int dx = 0; dx < n; ++dx) s += __ldg(row + dx);
+    }
+  }
+  return s / (float)(n * n);
+}
+#endif
+
 struct BlurXYArgs {
   const float *src;
   float *dst;
@@ -236,6 +271,9 @@ struct BlurXYArgs {
   CellsView cells = {nullptr, nullptr, nullptr, nullptr, 0, 0};
   float4 *part = nullptr;
   int Vz = 0, N = 0, P = 0;
+  // winner-only backward: plane slot j*Vz + z holds the gradient plane of projection bmap[j]
+  // (bits_in and cells are indexed by the real projection, src / part by the slot)
+  const int *bmap = nullptr;
 };
 int launch_blur_xy(const BlurXYArgs &a, const float *tx, int kx, const float *ty, int ky,
                    cudaStream_t s);
@@ -259,10 +297,11 @@ int launch_blurz_drc_fwd(const DrcArgs &a, const float *tz, int kz, float *bsave
 int drc_scale_partial_blocks(int V);
 // a.grid = blurZ-ed grid saved by the forward (or the plain voxels when kz == 0)
 // zero_ints/n_zero (NULL ok): block 0 clears this int array (the finalize counters)
+// lg (NULL ok; fast ray state only): winner-only chain slots and the on-the-fly loss gradient
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
                          float *g_grid, float *scale_partials, int *zero_ints, int n_zero,
-                         cudaStream_t s);
+                         cudaStream_t s, const LossGrad *lg = nullptr);
 int launch_blur_z(const float *src, float *dst, int P, int Vz, int V, const float *tz, int kz,
                   cudaStream_t s);
 int launch_depth_from_probs(const float *probs, float *depth, int P, int Vz, int V,
@@ -274,9 +313,10 @@ int launch_depth_from_probs_bwd(const float *g_depth, float *g_probs, int P, int
 int launch_dropout_select(int P, int N_src, int M, uint64_t seed, int *sel, cudaStream_t s);
 int launch_select_points(const float *points, const int *sel, int P, int R, int N_src, int M, int C,
                          float *out, cudaStream_t s);
-// inv: [P,N_src] int scratch, used when sel != NULL
+// inv: [P,N_src] int scratch, used when sel != NULL.  bmap (NULL ok): g_rep / inv hold P chain
+// slots and slot j carries the gradient of projection bmap[j] (its row of sel).
 int launch_replica_reduce(const float *g_rep, const int *sel, int *inv, int P, int R, int N_src,
-                          int M, int C, float *g_cloud, cudaStream_t s);
+                          int M, int C, float *g_cloud, cudaStream_t s, const int *bmap = nullptr);
 
 // ---- point-feature (RGB) branch (feature.cu) -----------------------------------
 int feat_max_channels();
@@ -294,9 +334,13 @@ int launch_colour_bwd(const float *probs, const float *fgrid, const float *div, 
 
 // ---- candidate-selection projection loss (candidate_loss.cu) -----------------
 int candidate_loss_max_candidates();
+// winners / kcoef (NULL ok): winners[bv] = bv * C + argmin, kcoef[bv] = -2 w^2 coeff
 int launch_candidate_loss_fwd(const float *gt, const float *pred, const float *weights, int BV,
                               int C, int V, int G, float *all_loss, long long *min_idx,
-                              float *view_loss, cudaStream_t s);
+                              float *view_loss, cudaStream_t s, int *winners = nullptr,
+                              float *kcoef = nullptr, float coeff = 0.f);
+// loss[0] = coeff * sum(view_loss) in index order
+int launch_loss_total(const float *view_loss, int BV, float coeff, float *loss, cudaStream_t s);
 int launch_candidate_loss_bwd(const float *gt, const float *pred, const float *weights,
                               const long long *min_idx, const float *upstream, float coeff, int BV,
                               int C, int V, int G, float *g_pred, cudaStream_t s);

@@ -536,7 +536,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
                           const Taps<R> kz, const float *__restrict__ g_mask,
                           const float *__restrict__ g_depth, float *__restrict__ g_grid,
                           float *__restrict__ scale_partials, int *__restrict__ zero_ints,
-                          int n_zero) {
+                          int n_zero, const LossGrad lg) {
   constexpr int VZ = V, W = 2 * R + 1, L = FwdRingLen<R>::L, VV = V * V;
   constexpr int NBLK = (VZ + L - 1) / L, NFULL = VZ / L, NSTORE = VZ > R ? (VZ - R) / L : 0;
   constexpr uint32_t ROW_BYTES = kBwdThreads * sizeof(u64);
@@ -547,9 +547,13 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
   u64 *tile = reinterpret_cast<u64 *>(smraw);                              // [VZ][threads]
   uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + (size_t)VZ * ROW_BYTES);   // [NBLK]
   const int tid = threadIdx.x;
-  int b, yx, oi;
-  pair_index<V>(c, kBwdThreads, b, yx, oi);
-  const size_t col0 = (size_t)b * VZ * VV + yx;
+  // chain slot bj works on projection b (winner-only backward of render_loss: b = bmap[bj]); the
+  // saved state, the scale and the upstream gradients belong to b, the gradient grid to the slot
+  int bj, yx, oi;
+  pair_index<V>(c, kBwdThreads, bj, yx, oi);
+  const int b = lg.bmap ? __ldg(lg.bmap + bj) : bj;
+  oi += (b - bj) * VV;
+  const size_t col0 = (size_t)b * VZ * VV + yx, colo = (size_t)bj * VZ * VV + yx;
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < NBLK; ++i) mbar_init(bars + i, 1);
@@ -578,7 +582,17 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
 #pragma unroll
   for (int i = 1; i < NBLK; ++i)
     tstart[i] = __ldg(reinterpret_cast<const u64 *>(tck + ((size_t)b * ck_slots + (i - 1)) * VV + yx));
-  const float2 gm = g_mask ? __ldg(reinterpret_cast<const float2 *>(g_mask + oi)) : make_float2(0.f, 0.f);
+  float2 gm = g_mask ? __ldg(reinterpret_cast<const float2 *>(g_mask + oi)) : make_float2(0.f, 0.f);
+  if (lg.gt) {
+    // dL/dmask of the candidate-selection loss for the winner, built here instead of read:
+    // k (pool(gt) - pred), rounded like candidate_loss_bwd_kernel (model_pc_to.py:430-437)
+    const int bv = b / lg.C, pix = oi - b * VV, yo = pix / V, xo = pix - yo * V, n = lg.G / V;
+    const float k = __ldg(lg.kcoef + bv) * (lg.upstream ? __ldg(lg.upstream) : 1.f);
+    const float2 pr = __ldg(reinterpret_cast<const float2 *>(lg.pred + oi));
+    const float *g = lg.gt + (size_t)bv * lg.G * lg.G;
+    gm.x = k * (pooled_gt(g, lg.G, n, yo, xo) - pr.x);
+    gm.y = k * (pooled_gt(g, lg.G, n, yo, xo + 1) - pr.y);
+  }
   const float2 gd = g_depth ? __ldg(reinterpret_cast<const float2 *>(g_depth + oi)) : make_float2(0.f, 0.f);
   u64 D2 = mul2(pack2(c.max_depth * gd.x, c.max_depth * gd.y), ec2);
   u64 ds2 = 0;
@@ -608,7 +622,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
         if (full || z0 + j < VZ) T2 = mul2(T2, fma2(abs2(col[(z0 + j) * kBwdThreads]), neg2, one2));
       }
     }
-    float *gout = g_grid + col0 + (size_t)(z0 + R) * VV;               // row z = k + R at j = 0
+    float *gout = g_grid + colo + (size_t)(z0 + R) * VV;               // row z = k + R at j = 0
     const float kf0 = (float)z0;
 #pragma unroll
     for (int j = L - 1; j >= 0; --j) {
@@ -652,7 +666,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
   }
   if (R > 0) {
     // flush: inputs k = -1 .. -R are zero; they complete the outputs z = R-1 .. 0
-    float *gout = g_grid + col0;
+    float *gout = g_grid + colo;
 #pragma unroll
     for (int j = L - 1; j >= L - R; --j) {
       ring[j] = 0;
@@ -806,7 +820,8 @@ static void launch_bwd_one(const DrcArgs &a, const RayConst &c, const Taps<R> &t
 template <int V, int R>
 static void launch_bwd_fast(const DrcArgs &a, const RayConst &c, const Taps<R> &taps,
                             const float *g_mask, const float *g_depth, float *g_grid,
-                            float *scale_partials, int *zero_ints, int n_zero, cudaStream_t s) {
+                            float *scale_partials, int *zero_ints, int n_zero, cudaStream_t s,
+                            const LossGrad &lg) {
   constexpr int L = FwdRingLen<R>::L, NBLK = (V + L - 1) / L;
   static_assert(NBLK * sizeof(uint64_t) <= 128, "mbarrier area");
   const size_t smem = (size_t)V * kBwdThreads * sizeof(u64) + 128;
@@ -818,15 +833,19 @@ static void launch_bwd_fast(const DrcArgs &a, const RayConst &c, const Taps<R> &
   const int blocks = a.P * (V * V / 2) / kBwdThreads;
   drc_blurz_bwd_fast_kernel<V, R><<<blocks, kBwdThreads, smem, s>>>(
       a.grid, a.tck, a.ck_slots, a.scale, c, taps, g_mask, g_depth, g_grid,
-      a.scale ? scale_partials : nullptr, zero_ints, n_zero);
+      a.scale ? scale_partials : nullptr, zero_ints, n_zero, lg);
 }
 
 int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float *g_mask,
                          const float *g_depth, const float *g_probs, const float *g_voxels,
                          float *g_grid, float *scale_partials, int *zero_ints, int n_zero,
-                         cudaStream_t s) {
+                         cudaStream_t s, const LossGrad *lg) {
   const RayConst c = make_ray_const(a);
   const int r = z_radius(tz, kz);
+  if (lg && !a.tck) {
+    set_error("drc_blurz_bwd: the winner-only / fused-loss backward needs the fast ray state");
+    return DPC_ERR_ARG;
+  }
   if (a.tck) {
     if (g_probs || g_voxels || a.Vz != a.V || !a.logsum) {
       set_error("drc_blurz_bwd: fast ray state needs a cubic grid, log-sum DRC and no g_probs / g_voxels");
@@ -834,7 +853,8 @@ int launch_drc_blurz_bwd(const DrcArgs &a, const float *tz, int kz, const float 
     }
     DPC_DISPATCH_V(a.V, DPC_DISPATCH_R(r, launch_bwd_fast<V, R>(a, c, z_taps<R>(tz, kz, r), g_mask,
                                                                 g_depth, g_grid, scale_partials,
-                                                                zero_ints, n_zero, s)));
+                                                                zero_ints, n_zero, s,
+                                                                lg ? *lg : LossGrad())));
     return check_launch("drc_blurz_bwd_fast");
   }
   if (g_probs || g_voxels) {

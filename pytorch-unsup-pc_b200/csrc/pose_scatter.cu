@@ -434,12 +434,13 @@ struct FinalizeArgs {
   float *g_quat, *g_trans, *g_focal, *g_scale;
 };
 
+// (bj: the chain slot whose partials belong to projection b; bj == b outside render_loss)
 __device__ __forceinline__ void finalize_projection(const PoseArgs &a, const FinalizeArgs &f,
-                                                    int b, int lane) {
+                                                    int b, int bj, int lane) {
   if (f.pose_partials) {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = lane; k < f.pose_blocks; k += 32) {
-      const double *p = f.pose_partials + ((size_t)b * f.pose_blocks + k) * 8;
+      const double *p = f.pose_partials + ((size_t)bj * f.pose_blocks + k) * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += __ldcg(p + i);
     }
@@ -465,14 +466,14 @@ __device__ __forceinline__ void finalize_projection(const PoseArgs &a, const Fin
   if (f.scale_partials && f.g_scale) {
     double v = 0;
     for (int k = lane; k < f.scale_blocks; k += 32)
-      v += (double)__ldcg(f.scale_partials + (size_t)b * f.scale_blocks + k);
+      v += (double)__ldcg(f.scale_partials + (size_t)bj * f.scale_blocks + k);
     v = warp_sum(v);
     if (lane == 0) f.g_scale[b] = (float)v;
   }
 }
 
 __global__ void finalize_kernel(PoseArgs a, FinalizeArgs f) {
-  finalize_projection(a, f, blockIdx.x, threadIdx.x);
+  finalize_projection(a, f, blockIdx.x, blockIdx.x, threadIdx.x);
 }
 
 // Sum of 8 per-lane fp64 values over the warp with 9 exchanges instead of 40: a
@@ -511,7 +512,10 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
                        CellsView cells, const float4 *__restrict__ part) {
   pdl_wait();             // the per-plane partial gathers come from the blur-XY adjoint
   pdl_release();
-  const int b = blockIdx.y;
+  // chain slot bj works on projection b (winner-only backward: b = bmap[bj]); inputs and the
+  // saved records belong to b, the partial gathers, the point gradients and the partials to bj
+  const int bj = blockIdx.y;
+  const int b = a.bmap ? __ldg(a.bmap + bj) : bj;
   const Quat q = block_quat(a.quat + 4 * b);
   const bool has_t = a.trans != nullptr;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
@@ -534,7 +538,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     for (int it = 0; it < kBwdPts; ++it) {
       const int n = (blockIdx.x * kBwdPts + it) * kBwdThreads + threadIdx.x;
       if (n >= a.N) continue;
-      const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+      const size_t pi = ((size_t)bj * a.N + n) * 3, si = point_offset(a, b, n);
       const float p0 = a.points[si], p1 = a.points[si + 1], p2 = a.points[si + 2];
       // p' = q^ (0,p) q^* (+ t), zc = p'0 + camera distance
       const float aw = -(vx * p0 + vy * p1 + vz * p2);
@@ -548,7 +552,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
       // part[0] = plane iz, part[1] = plane iz + 1 (absent when iz + 1 == Vz)
       // (both partials are loaded unconditionally, next to the z-cell byte, and
       // SELECTED afterwards: an unwritten slot may hold anything, NaN included)
-      const size_t idx = (size_t)b * a.N + n;
+      const size_t idx = (size_t)bj * a.N + n;
       const unsigned iz = cells.cellz[(size_t)b * cells.Npad + n];
       const float4 s0 = ld_dep(part + idx), s1 = ld_dep(part + (size_t)a.P * a.N + idx);
       const bool in0 = iz != kCellNone, in1 = in0 && (int)iz + 1 < a.Vz;
@@ -593,7 +597,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
   for (int it = 0; it < kBwdPts; ++it) {
     const int n = (blockIdx.x * kBwdPts + it) * kBwdThreads + threadIdx.x;
     if (n >= a.N) continue;
-    const size_t pi = ((size_t)b * a.N + n) * 3, si = point_offset(a, b, n);
+    const size_t pi = ((size_t)bj * a.N + n) * 3, si = point_offset(a, b, n);
     const double p0 = a.points[si], p1 = a.points[si + 1], p2 = a.points[si + 2];
     const PosePoint pp = pose_point(q, (float)p0, (float)p1, (float)p2, has_t, t0, t1, t2, f,
                                     a.cam_dist);
@@ -644,7 +648,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
     double v = 0;
 #pragma unroll
     for (int wdx = 0; wdx < kBwdThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
-    partials[((size_t)b * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
+    partials[((size_t)bj * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
     // publish the row before the arrival counter is bumped; only the writers fence
     // (a CTA-wide fence also waits for every warp's g_points stores: 25 % of this kernel)
     if (counters) __threadfence();
@@ -656,11 +660,11 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
   if (counters) {
     __shared__ int is_last;
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(counters + b, 1) == (int)gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(counters + bj, 1) == (int)gridDim.x - 1);
     __syncthreads();
     if (is_last && threadIdx.x < 32) {
       __threadfence();
-      finalize_projection(a, fin, b, threadIdx.x);
+      finalize_projection(a, fin, b, bj, threadIdx.x);
     }
   }
 }

@@ -139,10 +139,11 @@ select_points_kernel(const float *__restrict__ points, const int *__restrict__ s
 
 // inv[b][sel[b][m]] = m   (inv pre-filled with -1)
 __global__ void __launch_bounds__(256)
-invert_selection_kernel(const int *__restrict__ sel, int N_src, int M, int *__restrict__ inv) {
-  const int b = blockIdx.y, m = blockIdx.x * 256 + threadIdx.x;
+invert_selection_kernel(const int *__restrict__ sel, const int *__restrict__ bmap, int N_src, int M,
+                        int *__restrict__ inv) {
+  const int b = blockIdx.y, m = blockIdx.x * 256 + threadIdx.x;     // b: chain slot
   if (m >= M) return;
-  const int src = __ldg(sel + (size_t)b * M + m);
+  const int src = __ldg(sel + (size_t)(bmap ? __ldg(bmap + b) : b) * M + m);
   if ((unsigned)src < (unsigned)N_src) inv[(size_t)b * N_src + src] = m;   // never outside inv
 }
 
@@ -179,11 +180,11 @@ int launch_select_points(const float *points, const int *sel, int P, int R, int 
 }
 
 int launch_replica_reduce(const float *g_rep, const int *sel, int *inv, int P, int R, int N_src,
-                          int M, int C, float *g_cloud, cudaStream_t s) {
+                          int M, int C, float *g_cloud, cudaStream_t s, const int *bmap) {
   if (sel) {
     if (cudaMemsetAsync(inv, 0xFF, (size_t)P * N_src * sizeof(int), s) != cudaSuccess)
       return check_launch("memset(inv)");
-    invert_selection_kernel<<<dim3((M + 255) / 256, P), 256, 0, s>>>(sel, N_src, M, inv);
+    invert_selection_kernel<<<dim3((M + 255) / 256, P), 256, 0, s>>>(sel, bmap, N_src, M, inv);
     if (int e = check_launch("invert_selection")) return e;
   }
   replica_reduce_kernel<<<dim3((N_src + 255) / 256, P / R), 256, 0, s>>>(

@@ -266,6 +266,93 @@ def project(points, quat, trans, focal, scale, params, taps, want_voxels, want_p
     return mask, depth, tr_pc, voxels, probs
 
 
+class RenderLossFn(torch.autograd.Function):
+    """Replica-aware projection + candidate-selection loss as ONE op (model_pc_to.py:302-331 +
+    :339-385, 410-440): clouds, poses and ground-truth masks in, the loss out; the backward runs
+    over the winning candidate of every view only (the others' gradients are exactly zero) with
+    dL/dmask built inside the ray kernel.  Returns (loss [], min_idx [BV], all_loss [BV,C],
+    mask [P,V,V]); only ``loss`` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, points, quat, trans, focal, scale, masks, weights, params, taps, C,
+                weight_scale, mode, plane_local, replicas, N_src, sel):
+        lib = _lib.load()
+        dev = points.device
+        P, N, Vz, V = params.P, params.N, params.Vz, params.V
+        BV, G = masks.shape[0], masks.shape[-1]
+        params.outputs = 0
+        f32 = dict(dtype=torch.float32, device=dev)
+        mask = torch.empty(P, V, V, **f32)
+        all_loss = torch.empty(BV, C, **f32)
+        min_idx = torch.empty(BV, dtype=torch.int64, device=dev)
+        # view_loss [BV] | kcoef [BV] | loss [1] (fp32) and winners [BV] (int32), one allocation
+        small = torch.empty(3 * BV + 1, **f32)
+        view_loss, kcoef, loss = small[:BV], small[BV:2 * BV], small[2 * BV:2 * BV + 1]
+        winners = small[2 * BV + 1:].view(torch.int32)
+        use_cells = int(mode) == _lib.SCATTER_ATOMIC and plane_local
+        n_grid = P * Vz * V * V * 4
+        n_bits = P * Vz * V * (V // 32) * 4
+        n_cells = _sizes(params)[1] if use_cells else 0
+        state = torch.empty(n_grid + n_bits + n_cells, dtype=torch.uint8, device=dev)
+        base = state.data_ptr()
+        grid_b, bits = base, base + n_grid
+        cells = base + n_grid + n_bits if use_cells else None
+        ws = _workspace(params, dev)
+        with _on_device(dev):
+            st = lib.dpc_render_loss_fwd(
+                ctypes.byref(params), int(replicas), int(N_src), _ptr(sel), _ptr(points), _ptr(quat),
+                _ptr(trans), _ptr(focal), _ptr(scale), *_tap_args(taps), int(mode), int(C), int(G),
+                _ptr(masks), _ptr(weights), ctypes.c_float(weight_scale), grid_b, bits, cells,
+                _ptr(mask), _ptr(all_loss), _ptr(min_idx), _ptr(view_loss), _ptr(loss),
+                _ptr(winners), _ptr(kcoef), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "render_loss_fwd")
+        ctx.save_for_backward(points, quat, trans, focal, scale, masks, weights, sel, state, mask,
+                              min_idx, small)
+        ctx.params, ctx.taps = params, taps
+        ctx.meta = (int(C), int(G), float(weight_scale), int(mode), int(replicas), int(N_src),
+                    n_grid, n_bits, use_cells)
+        ctx.mark_non_differentiable(min_idx, all_loss, mask)
+        return loss.reshape(()), min_idx, all_loss, mask
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_idx, _g_all, _g_mask):
+        lib = _lib.load()
+        (points, quat, trans, focal, scale, masks, weights, sel, state, mask, min_idx,
+         small) = ctx.saved_tensors
+        C, G, weight_scale, mode, replicas, N_src, n_grid, n_bits, use_cells = ctx.meta
+        params = ctx.params
+        dev = points.device
+        P, N, Vz, V = params.P, params.N, params.Vz, params.V
+        BV = P // C
+        kcoef, winners = small[BV:2 * BV], small[2 * BV + 1:].view(torch.int32)
+        base = state.data_ptr()
+        grid_b, bits = base, base + n_grid
+        cells = base + n_grid + n_bits if use_cells else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        upstream = _f32(g_loss, "grad_output").reshape(1)
+        slots = lib.dpc_render_loss_slots(ctypes.byref(params), C, 1 if use_cells else 0, mode)
+        g_grid = _scratch("g_grid", slots * Vz * V * V * 4, dev)
+        g_rep = _scratch("g_rep", slots * N * 12, dev)
+        inv = _scratch("inv", slots * N_src * 4, dev) if sel is not None else None
+        g_mask = _scratch("g_mask", P * V * V * 4, dev) if slots == P else None
+        g_points = torch.empty(points.shape, **f32)
+        g_quat = torch.empty(P, 4, **f32)
+        g_trans = torch.empty(P, 3, **f32) if trans is not None else None
+        g_focal = torch.empty(P, **f32) if focal is not None else None
+        g_scale = torch.empty(P, **f32) if scale is not None else None
+        ws = _workspace(params, dev)
+        with _on_device(dev):
+            st = lib.dpc_render_loss_bwd(
+                ctypes.byref(params), replicas, N_src, _ptr(sel), _ptr(points), _ptr(quat),
+                _ptr(trans), _ptr(focal), _ptr(scale), *_tap_args(ctx.taps), mode, C, G,
+                _ptr(masks), _ptr(weights), ctypes.c_float(weight_scale), grid_b, bits, cells,
+                _ptr(mask), _ptr(min_idx), _ptr(winners), _ptr(kcoef), _ptr(upstream),
+                _ptr(g_grid), _ptr(g_rep), _ptr(inv), _ptr(g_mask), _ptr(g_points), _ptr(g_quat),
+                _ptr(g_trans), _ptr(g_focal), _ptr(g_scale), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "render_loss_bwd")
+        return (g_points, g_quat, g_trans, g_focal, g_scale) + (None,) * 11
+
+
 class PoseFn(torch.autograd.Function):
     """pc_perspective_transform (point_cloud_to.py:118-178, quaternion branch)."""
 

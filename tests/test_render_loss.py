@@ -1,0 +1,166 @@
+"""The renderer and its loss as one step (rows f2 -> path -> f1 fused;
+``pytorch_unsup_pc_b200.project_candidates_loss`` over dpc_render_loss_fwd / _bwd).
+
+CPU: the oracle composition against vectors made by the REAL reference's own composition
+(tests/golden/make_golden_render_loss.py).  GPU: the fused op against the same vectors
+(loss / projections 1e-5, gradients 1e-4, argmin equal), against the composition of the three
+separate CUDA ops (bit-identical: same kernels, same winner arithmetic, the skipped candidates'
+gradients are exact zeros), with the two half-chains of the winner-only backward (>= 64 views)
+and through the general saved-state path (deterministic scatter).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _golden
+from golden.make_golden_render_loss import CASES
+from oracle import render_loss as ORL
+from oracle.config import default_cfg
+
+GOLD = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                 "render_loss.npz")))
+
+
+def _case(name, device="cpu"):
+    spec = CASES[name]
+    cfg = default_cfg(pose_predict_num_candidates=spec["cands"], variable_num_views=spec["weights"],
+                      **spec["cfg"])
+    t = {k: torch.from_numpy(GOLD[name + "/in_" + k]).to(device) for k in ("points", "quat", "scale")}
+    t["masks"] = torch.from_numpy(GOLD[name + "/in_masks"]).float().to(device)
+    t["weights"] = (torch.from_numpy(GOLD[name + "/in_weights"]).to(device)
+                    if name + "/in_weights" in GOLD else None)
+    kx, ky, kz = (torch.from_numpy(GOLD[name + "/taps_" + k]) for k in "xyz")
+    kernel = [kx.reshape(1, 1, 1, 1, -1), ky.reshape(1, 1, 1, -1, 1), kz.reshape(1, 1, -1, 1, 1)]
+    idx = torch.from_numpy(GOLD[name + "/indices"]).long().to(device) if name + "/indices" in GOLD else None
+    return spec, cfg, t, kernel, idx
+
+
+def _pairs(idx):
+    P, M = idx.shape
+    return torch.stack([torch.arange(P).reshape(P, 1).expand(P, M), idx.cpu()], dim=-1)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_golden(name):
+    spec, cfg, t, kernel, idx = _case(name)
+    leaves = [t[k].clone().requires_grad_() for k in ("points", "quat", "scale")]
+    loss, min_loss, proj = ORL.project_candidates_loss(
+        cfg, leaves[0], leaves[1], t["masks"], spec["cands"], kernel, leaves[2],
+        weight_scale=spec["wscale"], valid_samples=t["weights"],
+        indices=None if idx is None else _pairs(idx))
+    assert loss.item() == pytest.approx(float(GOLD[name + "/loss"]), rel=1e-12)
+    assert min_loss.tolist() == GOLD[name + "/min_loss"].tolist()
+    assert _golden.rel_err(proj.float(), GOLD[name + "/proj"]) < 1e-7
+    for k, g in zip(("points", "quat", "scale"), torch.autograd.grad(loss, leaves)):
+        assert _golden.rel_err(g, GOLD[name + "/grad_" + k]) < 2e-6, k
+
+
+def test_host_validation():
+    import pytorch_unsup_pc_b200 as dpc
+    cfg = default_cfg(vox_size=32, pose_predict_num_candidates=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dpc.project_candidates_loss(cfg, torch.zeros(2, 10, 3), torch.zeros(4, 4), None,
+                                    torch.zeros(2, 1, 32, 32))
+    with pytest.raises(NotImplementedError):
+        dpc.project_candidates_loss(default_cfg(vox_size=32, pose_predict_num_candidates=1),
+                                    torch.zeros(2, 10, 3), torch.zeros(4, 4), None,
+                                    torch.zeros(2, 1, 32, 32))
+
+
+# ---------------------------------------------------------------------------- GPU
+def _fused(dpc, cfg, spec, t, kernel, idx):
+    leaves = [t[k].clone().requires_grad_() for k in ("points", "quat", "scale")]
+    out = dpc.project_candidates_loss(cfg, leaves[0], leaves[1], None, t["masks"], kernel,
+                                      scaling_factor=leaves[2], weight_scale=spec["wscale"],
+                                      valid_samples=t["weights"], indices=idx)
+    grads = torch.autograd.grad(out["loss"], leaves)
+    return out, grads
+
+
+def _composed(dpc, cfg, spec, t, kernel, idx):
+    leaves = [t[k].clone().requires_grad_() for k in ("points", "quat", "scale")]
+    dpc.set_outputs(voxels=False, drc_probs=False)
+    try:
+        proj = dpc.pointcloud_project_replicated(cfg, leaves[0], leaves[1], None, None, kernel,
+                                                 scaling_factor=leaves[2], indices=idx)["proj"]
+    finally:
+        dpc.set_outputs(voxels=True, drc_probs=True)
+    inputs = {"masks": t["masks"]}
+    if t["weights"] is not None:
+        inputs["valid_samples"] = t["weights"]
+    total, min_loss = dpc.add_proj_loss(cfg, inputs, {"projs": proj}, spec["wscale"])
+    grads = torch.autograd.grad(total, leaves)
+    return total, min_loss, proj, grads
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_cuda_matches_golden(name, deterministic):
+    """deterministic=True runs the sort-then-segment scatter, whose saved state is the general
+    layout: the fused op then writes dL/dmask for all P projections and runs the general
+    backward -- the same results through the other path."""
+    import pytorch_unsup_pc_b200 as dpc
+    spec, cfg, t, kernel, idx = _case(name, torch.device("cuda:0"))
+    with dpc.options(deterministic=deterministic):
+        out, grads = _fused(dpc, cfg, spec, t, kernel, idx)
+    assert abs(out["loss"].item() - float(GOLD[name + "/loss"])) <= 1e-5 * abs(float(GOLD[name + "/loss"]))
+    assert out["min_loss"].tolist() == GOLD[name + "/min_loss"].tolist()
+    assert _golden.rel_err(out["projs"], GOLD[name + "/proj"]) < 1e-5
+    assert grads[0].shape == t["points"].shape
+    for k, g in zip(("points", "quat", "scale"), grads):
+        assert _golden.rel_err(g, GOLD[name + "/grad_" + k].reshape(g.shape)) < 1e-4, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fused_equals_composition_of_the_three_ops(name):
+    import pytorch_unsup_pc_b200 as dpc
+    spec, cfg, t, kernel, idx = _case(name, torch.device("cuda:0"))
+    out, grads = _fused(dpc, cfg, spec, t, kernel, idx)
+    total, min_loss, proj, cgrads = _composed(dpc, cfg, spec, t, kernel, idx)
+    assert torch.equal(out["projs"], proj)
+    assert torch.equal(out["min_loss"], min_loss)
+    assert abs(out["loss"].item() - total.item()) <= 2e-6 * abs(total.item())   # summation order
+    for k, a, b in zip(("points", "quat", "scale"), grads, cgrads):
+        assert torch.equal(a, b), (k, (a - b).abs().max().item())
+    # the losing candidates' pose gradients are exact zeros
+    C = spec["cands"]
+    lose = torch.ones(t["quat"].shape[0], dtype=torch.bool, device=proj.device)
+    lose[torch.arange(min_loss.numel(), device=proj.device) * C + min_loss] = False
+    assert float(grads[1][lose].abs().max()) == 0.0 and float(grads[2][lose].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,views,C,N,V,keep", [(16, 4, 2, 300, 32, 1.0), (32, 2, 4, 257, 32, 0.6),
+                                                (16, 1, 4, 8000, 64, 1.0)])
+def test_large_batches_two_half_chains(B, views, C, N, V, keep):
+    """>= 64 projections: the forward runs as two half-batches; >= 64 views: the winner-only
+    backward runs as two half-chains.  Workload-A shapes (16 clouds x 4 candidates, 8000 points,
+    64^3) included.  Checked against the composition of the separate ops."""
+    import pytorch_unsup_pc_b200 as dpc
+    from oracle import closed_form as CF
+    dev = torch.device("cuda:0")
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=21 if V == 64 else 11,
+                      pose_predict_num_candidates=C)
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    P, BV = B * views * C, B * views
+    t = {"points": ((torch.rand(B, N, 3, generator=g) - 0.5) * 0.9).to(dev),
+         "quat": torch.randn(P, 4, generator=g).to(dev),
+         "scale": (0.2 + 0.8 * torch.rand(P, 1, generator=g)).to(dev),
+         "masks": (torch.rand(BV, 1, 2 * V, 2 * V, generator=g) > 0.6).float().to(dev),
+         "weights": None}
+    kernel = CF.smoothing_taps(cfg, 3.0 if V == 64 else 1.5)
+    spec = {"wscale": 1.0, "cands": C}
+    idx = None
+    if keep < 1:
+        from pytorch_unsup_pc_b200 import ops
+        idx = ops.dropout_indices(P, N, int(N * keep), 77, dev)
+    out, grads = _fused(dpc, cfg, spec, t, kernel, idx)
+    total, min_loss, proj, cgrads = _composed(dpc, cfg, spec, t, kernel, idx)
+    assert torch.equal(out["projs"], proj) and torch.equal(out["min_loss"], min_loss)
+    assert abs(out["loss"].item() - total.item()) <= 2e-6 * abs(total.item())
+    for k, a, b in zip(("points", "quat", "scale"), grads, cgrads):
+        assert torch.equal(a, b), (k, (a - b).abs().max().item())
