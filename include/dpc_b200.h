@@ -393,6 +393,13 @@ DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const 
                     void *workspace, size_t workspace_bytes, void *stream,
                     int iters, float *stage_ms_host);
 
+/* Measurement helper (bench.py roofline.fp32_frac): one launch of an FFMA2-only kernel -- the
+ * packed inner product of the blur kernels without its loads -- of blocks x 256 threads x iters
+ * x 21 taps x 16 scalar FMAs; *fma_count_host (NULL ok) receives that count.  The caller times it
+ * with CUDA events.  out: blocks * 256 floats of scratch. */
+DPC_API int dpc_fma_rate_probe(int blocks, int iters, float *out, double *fma_count_host,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -902,7 +902,7 @@ static int render_bwd_range(const dpc_params *p, int j0, int n, const BwdPtrs &q
       pa, b.cells, part, nullptr, q.g_points + j0 * N3, w.pose_partials + (size_t)j0 * ppb * 8,
       w.counters + j0, q.scale ? w.scale_partials + (size_t)j0 * spb : nullptr, spb, q.g_quat,
       (q.trans && q.g_trans) ? q.g_trans : nullptr, (q.focal && q.g_focal) ? q.g_focal : nullptr,
-      (q.scale && q.g_scale) ? q.g_scale : nullptr, s));
+      (q.scale && q.g_scale) ? q.g_scale : nullptr, s, lg.C));
   stage_mark(s);
   return DPC_OK;
 }
@@ -945,12 +945,8 @@ int dpc_render_loss_bwd(const dpc_params *p, int replicas, int N_src, const int3
   DPC_TRY(check_taps(tz, kz, "taps_z"));
   DPC_TRY(check_ws(p, workspace, workspace_bytes));
   const Workspace w = carve(p, workspace);
-  // pose gradients of the losing candidates: exactly zero
-  bool ok = cudaMemsetAsync(g_quat, 0, (size_t)p->P * 4 * sizeof(float), s) == cudaSuccess;
-  if (trans && g_trans) ok = ok && cudaMemsetAsync(g_trans, 0, (size_t)p->P * 3 * sizeof(float), s) == cudaSuccess;
-  if (focal && g_focal) ok = ok && cudaMemsetAsync(g_focal, 0, (size_t)p->P * sizeof(float), s) == cudaSuccess;
-  if (scale && g_scale) ok = ok && cudaMemsetAsync(g_scale, 0, (size_t)p->P * sizeof(float), s) == cudaSuccess;
-  if (!ok) return check_launch("render_loss_bwd: memset");
+  // (the pose gradients of the losing candidates, exact zeros, are written by the winners'
+  // finalize in the last kernel of the chain: no memset nodes on the critical path)
   Replica rep;
   rep.replicas = replicas; rep.N_src = N_src; rep.sel = sel;
   LossGrad lg;

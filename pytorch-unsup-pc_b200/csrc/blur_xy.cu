@@ -267,7 +267,10 @@ __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
          (v.w <= 1.f ? 8u : 0u);
 }
 
-template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT, bool POINTS>
+// SLOTS: the winner-only backward of render_loss (plane slots addressed through bmap).  A
+// template parameter, not a run-time branch: at 56 registers (9 CTAs per SM) the slot / plane
+// index pair costs the plain kernel 2.7 us per launch (47.1 vs 44.4 us at workload A).
+template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT, bool POINTS, bool SLOTS = false>
 __global__ void __launch_bounds__(XYCfg<V, R>::THREADS, XYCfg<V, R>::MINB)
 blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                uint32_t *__restrict__ bits_out, const uint32_t *__restrict__ bits_in,
@@ -290,8 +293,9 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   // (winner-only backward: the launch covers chain slots; slot pj holds the gradient planes of
   // projection pb = bmap[pj] -- src / part are indexed by the slot, bits_in / cells by pb)
   const int pj = POINTS ? (int)(plane / Vz) : 0, pz = POINTS ? (int)(plane - (size_t)pj * Vz) : 0;
-  const int pb = (POINTS && MASK_OUT && bmap) ? __ldg(bmap + pj) : pj;
-  const size_t bplane = POINTS ? (size_t)pb * Vz + pz : plane;      // plane index of the clamp bits
+  static_assert(!SLOTS || (POINTS && MASK_OUT), "SLOTS: plane-gather backward only");
+  const int pb = SLOTS ? __ldg(bmap + pj) : pj;
+  const size_t bplane = SLOTS ? (size_t)pb * Vz + pz : plane;       // plane index of the clamp bits
   TouchRange touch = {0u, 0u, 0u, nullptr};
   uint4 rec0 = make_uint4(0u, 0u, 0u, 0u);
   if (POINTS && DPC_XY_PREFETCH) {
@@ -584,18 +588,18 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
   using C = XYCfg<V, R>;
   const Taps<R> KX = make_taps<R>(tx, kx), KY = make_taps<R>(ty, ky);
   dim3 g(a.planes), t(C::THREADS);
-#define DPC_LAUNCH_XY(CL, WB, MO, PT)                                                          \
+#define DPC_LAUNCH_XY(CL, WB, MO, PT, ...)                                                     \
   do {                                                                                         \
     /* the gather tile lives behind the window tiles when it cannot overlay them */            \
     const size_t smem = C::SMEM + ((PT && MO && C::YTASKS != C::THREADS) ? V * V * 4 : 0) +    \
                         ((PT && WB) ? C::RH * V / 8 : 0) + ((MO && DPC_XY_BITS_SMEM) ? V * V / 8 : 0); \
     static DeviceOnce attr_once;                                                               \
     if (attr_once.first()) {                                                                   \
-      cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT>,                               \
+      cudaFuncSetAttribute(blur_xy_kernel<V, R, CL, WB, MO, PT, ##__VA_ARGS__>,                \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     }                                                                                          \
-    launch_dep(blur_xy_kernel<V, R, CL, WB, MO, PT>, g, t, smem, s, a.src, a.dst, a.bits_out,  \
-               a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P, a.bmap);                    \
+    launch_dep(blur_xy_kernel<V, R, CL, WB, MO, PT, ##__VA_ARGS__>, g, t, smem, s, a.src,      \
+               a.dst, a.bits_out, a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P, a.bmap); \
   } while (0)
   const bool points = a.cells.cellz != nullptr;
   if (points && (a.Vz < 1 || a.N < 1 || a.P < 1 || (!a.bits_in && !a.bits_out) ||
@@ -603,8 +607,13 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
     set_error("blur_xy: plane-local scatter/gather needs Vz, N, P and bits (and part backward)");
     return DPC_ERR_ARG;
   }
+  if (a.bmap && !(points && a.bits_in)) {
+    set_error("blur_xy: plane slots (bmap) exist on the plane-gather backward only");
+    return DPC_ERR_ARG;
+  }
   if (a.bits_in) {
-    if (points) DPC_LAUNCH_XY(false, false, true, true);
+    if (points && a.bmap) DPC_LAUNCH_XY(false, false, true, true, true);
+    else if (points) DPC_LAUNCH_XY(false, false, true, true);
     else DPC_LAUNCH_XY(false, false, true, false);
   } else if (a.bits_out) {
     if (!a.clamp_in) { set_error("blur_xy: bits_out requires clamp_in"); return DPC_ERR_ARG; }

@@ -84,8 +84,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // data is read-only for the whole lifetime of the reading grid, and under a programmatic launch
 // this grid is already resident while the primary is still writing.  __ldg stays on true inputs
 // (points, taps, upstream gradients, the forward's saved state in the backward).
+#ifndef DPC_LD_DEP_NC
+#define DPC_LD_DEP_NC 0        // A/B: 1 = the old ld.global.nc on these loads (timing only)
+#endif
 template <typename T>
-__device__ __forceinline__ T ld_dep(const T *p) { return __ldcg(p); }
+__device__ __forceinline__ T ld_dep(const T *p) { return DPC_LD_DEP_NC ? __ldg(p) : __ldcg(p); }
 #ifndef DPC_PDL_EARLY
 #define DPC_PDL_EARLY 0
 #endif
@@ -193,7 +196,7 @@ int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const fl
                              const float *g_trpc, float *g_points, double *partials,
                              int *counters, const float *scale_partials, int scale_blocks,
                              float *g_quat, float *g_trans, float *g_focal, float *g_scale,
-                             cudaStream_t s);
+                             cudaStream_t s, int winner_of_cands = 0);
 
 // pose (+ optional scatter into `grid`): tr_pc may be NULL when grid != NULL.
 int launch_pose_scatter(const PoseArgs &a, float *tr_pc, float *grid, cudaStream_t s);

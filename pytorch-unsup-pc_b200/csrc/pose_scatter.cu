@@ -432,6 +432,9 @@ struct FinalizeArgs {
   const float *scale_partials;   // [P][scale_blocks]   or NULL
   int pose_blocks, scale_blocks;
   float *g_quat, *g_trans, *g_focal, *g_scale;
+  // winner-only backward (render_loss): projection b is the winner among the `cands` candidates
+  // of its view; its finalize also writes the exact zeros of the losers' pose gradients.  0: off
+  int cands = 0;
 };
 
 // (bj: the chain slot whose partials belong to projection b; bj == b outside render_loss)
@@ -469,6 +472,15 @@ __device__ __forceinline__ void finalize_projection(const PoseArgs &a, const Fin
       v += (double)__ldcg(f.scale_partials + (size_t)bj * f.scale_blocks + k);
     v = warp_sum(v);
     if (lane == 0) f.g_scale[b] = (float)v;
+  }
+  if (f.cands > 1 && lane < f.cands) {
+    const int o = (b / f.cands) * f.cands + lane;      // a candidate of b's view
+    if (o != b) {
+      if (f.g_quat) *reinterpret_cast<float4 *>(f.g_quat + 4 * o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f.g_trans) f.g_trans[3 * o] = f.g_trans[3 * o + 1] = f.g_trans[3 * o + 2] = 0.f;
+      if (f.g_focal) f.g_focal[o] = 0.f;
+      if (f.g_scale) f.g_scale[o] = 0.f;
+    }
   }
 }
 
@@ -712,10 +724,14 @@ int launch_pose_bwd_partials(const PoseArgs &a, const CellsView &cells, const fl
                              const float *g_trpc, float *g_points, double *partials,
                              int *counters, const float *scale_partials, int scale_blocks,
                              float *g_quat, float *g_trans, float *g_focal, float *g_scale,
-                             cudaStream_t s) {
+                             cudaStream_t s, int winner_of_cands) {
   dim3 g(pose_partial_blocks(a.N), a.P), t(kBwdThreads);
   FinalizeArgs f{partials, scale_partials, pose_partial_blocks(a.N), scale_blocks,
-                 g_quat, g_trans, g_focal, g_scale};
+                 g_quat, g_trans, g_focal, g_scale, winner_of_cands};
+  if (winner_of_cands > 32) {
+    set_error("pose_bwd_partials: at most 32 candidates per view");
+    return DPC_ERR_ARG;
+  }
   launch_dep(gather_pose_bwd_kernel, g, t, 0, s, a, (const float *)nullptr, g_trpc, g_points,
              partials, counters, f, cells, part);
   return check_launch("pose_bwd_partials");

@@ -152,15 +152,16 @@ invert_selection_kernel(const int *__restrict__ sel, const int *__restrict__ bma
 __global__ void __launch_bounds__(256)
 replica_reduce_kernel(const float *__restrict__ g_rep, const int *__restrict__ inv, int R,
                       int N_src, int M, int C, float *__restrict__ g_cloud) {
+  pdl_wait();             // the per-replica gradients come from the pose adjoint (or inv from the inversion)
   const int c = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
   if (n >= N_src) return;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int r = 0; r < R; ++r) {
     const int b = c * R + r;
-    const int slot = inv ? __ldg(inv + (size_t)b * N_src + n) : n;
+    const int slot = inv ? ld_dep(inv + (size_t)b * N_src + n) : n;
     if (slot < 0) continue;
     const float *g = g_rep + ((size_t)b * M + slot) * C;
-    for (int k = 0; k < C; ++k) acc[k] += __ldg(g + k);
+    for (int k = 0; k < C; ++k) acc[k] += ld_dep(g + k);
   }
   float *o = g_cloud + ((size_t)c * N_src + n) * C;
   for (int k = 0; k < C; ++k) o[k] = acc[k];
@@ -187,8 +188,8 @@ int launch_replica_reduce(const float *g_rep, const int *sel, int *inv, int P, i
     invert_selection_kernel<<<dim3((M + 255) / 256, P), 256, 0, s>>>(sel, bmap, N_src, M, inv);
     if (int e = check_launch("invert_selection")) return e;
   }
-  replica_reduce_kernel<<<dim3((N_src + 255) / 256, P / R), 256, 0, s>>>(
-      g_rep, sel ? inv : nullptr, R, N_src, M, C, g_cloud);
+  launch_dep(replica_reduce_kernel, dim3((N_src + 255) / 256, P / R), dim3(256), 0, s, g_rep,
+             (const int *)(sel ? inv : nullptr), R, N_src, M, C, g_cloud);
   return check_launch("replica_reduce");
 }
 

@@ -10,7 +10,7 @@ out=$root/pytorch-unsup-pc_b200/lib/variants
 obj=$root/pytorch-unsup-pc_b200/build/variant_$name
 mkdir -p $out $obj
 flags="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr"
-for f in api pose_scatter blur_xy drc scatter_sorted candidate_loss chamfer replica feature; do
+for f in api pose_scatter blur_xy drc scatter_sorted candidate_loss chamfer replica feature microbench; do
   extra=""; [ $f = chamfer ] && extra="-fmad=false"   # see csrc/Makefile
   nvcc $flags $extra "$@" -c $src/$f.cu -o $obj/$f.o &
 done
