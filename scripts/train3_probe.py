@@ -89,6 +89,5 @@ def graphed(**ddp_kw):
 torch.backends.cudnn.benchmark = True
 graphed(single=True)
 graphed(gradient_as_bucket_view=True)
-graphed(gradient_as_bucket_view=True, bucket_cap_mb=8)
 graphed(gradient_as_bucket_view=True, bucket_cap_mb=100)
 dist.destroy_process_group()
