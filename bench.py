@@ -799,6 +799,64 @@ def bench_projection(env, key, full):
     return rec
 
 
+def bench_trajectory(env, key="A"):
+    """`value` along the training trajectory of the reference: sigma_rel falls 3.0 -> 0.2
+    (model_pc_to.py:59-63; the kernels run with the tap radius that holds all but 1e-7 of the taps)
+    while the point-dropout keep probability rises 0.07 -> 1.0 (:68-87; N_eff = 560 -> 8000).
+    Device-resident C-ABI steps replayed from a CUDA graph, this rank only (no fence)."""
+    import torch
+    from pytorch_unsup_pc_b200 import _lib, ops
+    dpc, lib, dev, stream = env.dpc, env.lib, env.dev, env.stream
+    out = []
+    for keep in (0.07, 0.5, 1.0):
+        for sigma in (3.0, 1.0, 0.5, 0.2):
+            w = dict(WORKLOADS[key], sigma=sigma, N=max(1, int(WORKLOADS[key]["N"] * keep)))
+            cfg = make_cfg(w)
+            P, N, V = w["P"], w["N"], w["V"]
+            taps = ops.host_taps(dpc.smoothing_kernel(cfg, sigma))
+            params = ops.make_params(cfg, P, N, flip_y=True)
+            d = {k: v.to(dev) for k, v in synth_inputs(w, 1000).items()}
+            f32 = dict(dtype=torch.float32, device=dev)
+            buf = dict(tr_pc=torch.empty(P, N, 3, **f32), grid=torch.empty(P, V, V, V, **f32),
+                       bits=torch.empty(P, V, V, V // 32, dtype=torch.int32, device=dev),
+                       mask=torch.empty(P, V, V, **f32), depth=torch.empty(P, V, V, **f32),
+                       g_grid=torch.empty(P, V, V, V, **f32), g_points=torch.empty(P, N, 3, **f32),
+                       g_quat=torch.empty(P, 4, **f32), g_scale=torch.empty(P, **f32),
+                       cells=torch.empty(lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev))
+            ws = torch.empty(lib.dpc_workspace_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev)
+            sptr = ctypes.c_void_p(stream.cuda_stream)
+            P_, ta = ops._ptr, ops._tap_args(taps)
+
+            def step(i):
+                _lib.check(lib.dpc_project_fwd(
+                    ctypes.byref(params), P_(d["points"]), P_(d["quat"]), None, None, P_(d["scale"]), *ta,
+                    _lib.SCATTER_ATOMIC, P_(buf["tr_pc"]), P_(buf["grid"]), P_(buf["bits"]), P_(buf["cells"]),
+                    P_(buf["mask"]), P_(buf["depth"]), None, None, P_(ws), ws.numel(), sptr), "project_fwd")
+                _lib.check(lib.dpc_project_bwd(
+                    ctypes.byref(params), P_(d["points"]), P_(d["quat"]), None, None, P_(d["scale"]), *ta,
+                    P_(buf["grid"]), P_(buf["bits"]), P_(buf["cells"]), P_(d["g_mask"]), P_(d["g_depth"]), None,
+                    None, None, P_(buf["g_grid"]), P_(buf["g_points"]), P_(buf["g_quat"]), None, None,
+                    P_(buf["g_scale"]), P_(ws), ws.numel(), sptr), "project_bwd")
+            g = env.graph_of(step, 3, sptr)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(12):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) / 36 * 1e3
+            out.append({"sigma": sigma, "keep_prob": keep, "N_eff": N,
+                        "tap_radius": lib.dpc_tap_radius(taps[0].data_ptr(), taps[0].numel()),
+                        "us_per_step": us, "value_per_gpu": P / us * 1e6})
+            del buf, ws, g, d
+    torch.cuda.empty_cache()
+    return {"unit": UNIT, "what": "device-resident fwd+bwd steps of workload %s shapes, one GPU (rank 0), "
+            "36 graph-replayed steps per point" % key, "points": out}
+
+
 def bench_fused(env, key, w, cfg, kern, taps, host, measure_e2e, g_steps, full):
     """The renderer + candidate-selection loss as one step (project_candidates_loss over
     dpc_render_loss_fwd / _bwd): clouds [B,N,3], poses [P,4], scales, ground-truth masks
@@ -951,6 +1009,8 @@ def run_b200(args, rank, world, local_rank):
     env.fma_peak = measure_fma_peak(env)
 
     main = bench_projection(env, args.workload, full=True)
+    if not args.main_only:
+        main["trajectory"] = bench_trajectory(env, args.workload if args.workload in ("A", "C3") else "A")
     subs = {}
     if args.workload == "A" and not args.main_only:
         for key in ("C3", "B", "C5"):

@@ -393,6 +393,13 @@ DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const 
                     void *workspace, size_t workspace_bytes, void *stream,
                     int iters, float *stage_ms_host);
 
+/* Host-side query: the tap radius the blur kernels run with for these n (odd) host taps -- the
+ * smallest radius outside of which the taps' total magnitude is <= 1e-7 (DPC_TAP_EPS in the
+ * environment overrides; 0 keeps every non-zero tap).  The reference's Gaussian always has
+ * pc_gauss_kernel_size taps (gauss_kernel.py:5-11) while sigma falls from 3.0 to 0.2 over training
+ * (model_pc_to.py:59-63); kernels are instantiated for radii 2 / 5 / 7 / 10 (Z pass also 0). */
+DPC_API int dpc_tap_radius(const float *taps_host, int n);
+
 /* Measurement helper (bench.py roofline.fp32_frac): one launch of an FFMA2-only kernel -- the
  * packed inner product of the blur kernels without its loads -- of blocks x 256 threads x iters
  * x 21 taps x 16 scalar FMAs; *fma_count_host (NULL ok) receives that count.  The caller times it

@@ -39,6 +39,16 @@ bool pdl_enabled() {
   return on;
 }
 
+// DPC_TAP_EPS (env): total tap magnitude effective_radius() may drop (default 1e-7; 0: none)
+float tap_truncation_eps() {
+  static const float eps = [] {
+    const char *e = getenv("DPC_TAP_EPS");
+    const double v = e ? atof(e) : 1e-7;
+    return (float)(v < 0 ? 0 : v);
+  }();
+  return eps;
+}
+
 static thread_local cudaEvent_t *tl_stage_events = nullptr;
 static thread_local int tl_stage_idx = 0;
 static inline void stage_mark(cudaStream_t s) {
@@ -392,6 +402,11 @@ int dpc_project_chunks(const dpc_params *p) {
   if (!p || p->P < 1) return 0;
   const int c = chunk_size(p);
   return c < p->P ? (p->P + c - 1) / c : 1;
+}
+
+int dpc_tap_radius(const float *taps_host, int n) {
+  if (!taps_host || n < 1 || n % 2 == 0) return -1;
+  return effective_radius(taps_host, n);
 }
 
 int dpc_project_kernels_per_chunk(const dpc_params *p) {

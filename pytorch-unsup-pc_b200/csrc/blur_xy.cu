@@ -639,7 +639,12 @@ static int launch_v(const BlurXYArgs &a, const float *tx, int kx, const float *t
   const float *px = kx > 0 ? tx + (ox > 0 ? ox : 0) : &one;
   const float *py = ky > 0 ? ty + (oy > 0 ? oy : 0) : &one;
   const int nx = kx > 0 ? (ox > 0 ? 2 * r + 1 : kx) : 1, ny = ky > 0 ? (oy > 0 ? 2 * r + 1 : ky) : 1;
+  // tap-radius templates: sigma_rel falls from 3.0 to 0.2 over training, and with it the radius
+  // that holds all but 1e-7 of the taps (effective_radius): 10 above sigma ~1.2, 7 down to ~0.95,
+  // 5 down to ~0.7, 2 below ~0.55
+  if (r <= 2) return launch_vr<V, 2>(a, px, nx, py, ny, s);
   if (r <= 5) return launch_vr<V, 5>(a, px, nx, py, ny, s);
+  if (r <= 7) return launch_vr<V, 7>(a, px, nx, py, ny, s);
   if (r <= 10) return launch_vr<V, 10>(a, px, nx, py, ny, s);
   set_error("blur_xy: tap radius %d > 10 unsupported", r);
   return DPC_ERR_ARG;

@@ -1,5 +1,6 @@
 // Shared declarations for the dpc_b200 kernels (sm_100a).
 #pragma once
+#include <cmath>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/dpc_b200.h"
@@ -30,16 +31,29 @@ inline Taps<R> make_taps(const float *host, int n) {
   return t;
 }
 
-// Smallest radius that holds all non-zero taps (taps that are exactly 0.0f
-// contribute nothing, so they can be dropped without changing a single bit).
+// Tap radius the kernels run with: the smallest radius outside of which the taps' total
+// magnitude is at most tap_truncation_eps() (default 1e-7; 0 keeps every non-zero tap; taps
+// that are exactly 0.0f never count).  The reference's Gaussian has K = 21 taps whatever sigma is
+// (gauss_kernel.py:5-11), while sigma runs from 3.0 down to 0.2 over training
+// (model_pc_to.py:59-63): at sigma = 1 the ten outermost taps together weigh 1.2e-8, at
+// sigma = 0.5 sixteen of them 2.4e-8.  The kept taps are used AS THEY ARE (no re-normalisation),
+// so a blur pass of values in [0, 1] moves by at most eps and the whole path by a few 1e-7 --
+// inside the 1e-5 forward tolerance with room to spare (tests/test_gpu_sweep.py, sigma schedule).
+// Forward and backward see the same taps (reversed), hence the same radius.
+float tap_truncation_eps();
 inline int effective_radius(const float *host, int n) {
   if (n <= 0) return 0;
-  int c = n / 2, r = 0;
-  for (int i = 0; i < n; ++i)
-    if (host[i] != 0.f) {
-      int d = i > c ? i - c : c - i;
-      if (d > r) r = d;
-    }
+  const int c = n / 2;
+  const double eps = (double)tap_truncation_eps();
+  double dropped = 0.0;
+  int r = c;
+  while (r > 0) {
+    // shrinking to radius r - 1 drops the two taps at distance r
+    const double d = fabs((double)host[c - r]) + fabs((double)host[c + r]);
+    if (dropped + d > eps) break;
+    dropped += d;
+    --r;
+  }
   return r;
 }
 

@@ -125,6 +125,7 @@ template <> struct RingLen<0> { static constexpr int L = 8; };
 template <> struct RingLen<5> { static constexpr int L = 16; };
 template <int R> struct FwdRingLen { static constexpr int L = RingLen<R>::L; };
 template <> struct FwdRingLen<0> { static constexpr int L = 16; };
+template <> struct FwdRingLen<7> { static constexpr int L = 24; };    // 16 steps of load-ahead, as at radius 10
 template <> struct FwdRingLen<10> { static constexpr int L = DPC_FWD_L10; };
 
 struct RayConst {
@@ -741,6 +742,7 @@ static Taps<R> z_taps(const float *tz, int kz, int r) {
     if (r == 0) { constexpr int R = 0; __VA_ARGS__; }                     \
     else if (r <= 2) { constexpr int R = 2; __VA_ARGS__; }                \
     else if (r <= 5) { constexpr int R = 5; __VA_ARGS__; }                \
+    else if (r <= 7) { constexpr int R = 7; __VA_ARGS__; }                \
     else if (r <= 10) { constexpr int R = 10; __VA_ARGS__; }              \
     else { set_error("z tap radius %d > 10 unsupported", r); return DPC_ERR_ARG; } \
   } while (0)

@@ -118,3 +118,24 @@ def test_dropout_selection_is_validated():
         pc._selection(torch.tensor([[0.0, 1.0, 2.0], [1.0, 4.0, 0.0]]), 2, 5, "cpu")
     with pc.options(validate_indices=False):
         pc._selection(torch.tensor([[0, 3, 3], [1, 4, 0]]), 2, 5, "cpu")
+
+
+def test_tap_radius_follows_sigma():
+    """The radius the blur kernels run with: all but 1e-7 of the taps' mass (no GPU needed)."""
+    import pytorch_unsup_pc_b200 as dpc
+    lib = dpc._lib.load()
+    cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
+    got = {}
+    for sigma in (3.0, 2.0, 1.3, 1.0, 0.8, 0.6, 0.4, 0.2):
+        taps = dpc.smoothing_kernel(cfg, sigma)[0].reshape(-1).contiguous()
+        r = lib.dpc_tap_radius(taps.data_ptr(), taps.numel())
+        dropped = float(taps.double()[: 10 - r].sum() + taps.double()[11 + r:].sum())
+        assert dropped <= 1e-7, (sigma, r, dropped)
+        if r > 0:      # one tap less would drop too much
+            assert dropped + 2 * float(taps[10 - r]) > 1e-7, (sigma, r)
+        got[sigma] = r
+    assert got[3.0] == 10 and got[2.0] == 10 and got[1.0] <= 6 and got[0.4] <= 2 and got[0.2] == 1, got
+    assert all(got[a] >= got[b] for a, b in zip(list(got)[:-1], list(got)[1:])), got
+    one = torch.ones(1)
+    assert lib.dpc_tap_radius(one.data_ptr(), 1) == 0
+    assert lib.dpc_tap_radius(one.data_ptr(), 2) == -1
