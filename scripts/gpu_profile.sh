@@ -5,9 +5,9 @@
 # usage: bash scripts/gpu_profile.sh <tag>     -> gpurun_out/launches_<tag>.csv, prof_<tag>.ncu-rep
 tag=${1:-rxx}
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+BENCH="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --main-only --no-parity-check --no-fused"
 $BENCH > gpurun_out/bench_$tag.json 2> gpurun_out/bench_${tag}_err.log || { echo "bench failed"; tail -5 gpurun_out/bench_${tag}_err.log; exit 1; }
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_$tag.csv $BENCH > gpurun_out/ncu_$tag.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/launches_$tag.csv)"
 DPC_CHUNK=100000 python scripts/profile_step.py --steps 2 > gpurun_out/plain_$tag.log 2>&1 || { echo "profile_step failed"; exit 1; }
