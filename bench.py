@@ -764,8 +764,8 @@ def bench_projection(env, key, full):
         # kernels per chunk: pose_bin (pose_cells + bin_points above 16384 points; pose_scatter on
         # the global-grid path), blur_xy, blurz_drc_fwd | drc_blurz_bwd, blur_xy, gather_pose_bwd
         # -- times the chunks the batch is split into (whole job: every rank launches its own);
-        # the deterministic mode: sort + segment kernels instead of pose_bin, + finalize
-        "gpu_launches": (7 if deterministic else 6 if args.global_grid else
+        # the deterministic mode: records + sort + segment kernels instead of pose_bin (8 per chunk)
+        "gpu_launches": (8 if deterministic else 6 if args.global_grid else
                          lib.dpc_project_kernels_per_chunk(ctypes.byref(params)))
                         * n_chunks * steps * world,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,

@@ -393,6 +393,13 @@ DPC_API int dpc_project_profile(const dpc_params *p, const float *points, const 
                     void *workspace, size_t workspace_bytes, void *stream,
                     int iters, float *stage_ms_host);
 
+/* The library allocates nothing and keeps no state -- with one exception: per host thread and
+ * device, the two internal side streams (and three events) of the half-batch split (batches of
+ * >= 64 projections), created on first use.  dpc_release() destroys the calling thread's set for
+ * the current device; call it after synchronising the work issued through the library (it is
+ * re-created on the next call that needs it).  Optional: the set is a few handles per thread. */
+DPC_API int dpc_release(void);
+
 /* Host-side query: the tap radius the blur kernels run with for these n (odd) host taps -- the
  * smallest radius outside of which the taps' total magnitude is <= 1e-7 (DPC_TAP_EPS in the
  * environment overrides; 0 keeps every non-zero tap).  The reference's Gaussian always has

@@ -382,6 +382,26 @@ static Pipeline *get_pipeline() {
   return &pl;
 }
 
+// The only state the library keeps: per host thread and device, two non-blocking side streams and
+// three events for the half-batch split, created on first use.  dpc_release() destroys the calling
+// thread's set for the current device (after the caller has synchronised the work it issued).
+static int release_pipeline() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DPC_OK;
+  Pipeline &pl = tl_pipe[dev];
+  if (!pl.ready) return DPC_OK;
+  for (int i = 0; i < 2; ++i) {
+    cudaStreamDestroy(pl.side[i]);
+    cudaEventDestroy(pl.join[i]);
+    pl.side[i] = nullptr;
+    pl.join[i] = nullptr;
+  }
+  cudaEventDestroy(pl.fork);
+  pl.fork = nullptr;
+  pl.ready = false;
+  return check_launch("release");
+}
+
 static int chunk_size(const dpc_params *p) {
   if (tl_force_single) return p->P;
   static int env_chunk = -1;
@@ -403,6 +423,8 @@ int dpc_project_chunks(const dpc_params *p) {
   const int c = chunk_size(p);
   return c < p->P ? (p->P + c - 1) / c : 1;
 }
+
+int dpc_release(void) { return release_pipeline(); }
 
 int dpc_tap_radius(const float *taps_host, int n) {
   if (!taps_host || n < 1 || n % 2 == 0) return -1;
@@ -494,7 +516,7 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   } else if (scatter_mode == DPC_SCATTER_SORTED) {
     stage_mark(s);
     DPC_TRY(launch_scatter_sorted(&pa, nullptr, n, p->N, p->Vz, p->V, tr_pc, grid,
-                                  (uint32_t *)w.sorted + (size_t)2 * b0 * p->N,
+                                  sorted_workspace_at(w.sorted, b0, p->N, p->Vz, p->V),
                                   sorted_workspace_bytes(n, p->N, p->Vz, p->V), s));
   } else {
     if (cudaMemsetAsync(grid, 0, (size_t)n * G * sizeof(float), s) != cudaSuccess)

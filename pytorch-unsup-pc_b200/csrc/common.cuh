@@ -223,6 +223,7 @@ int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N
                           float *tr_pc_out, float *grid, void *ws, size_t ws_bytes,
                           cudaStream_t s);
 size_t sorted_workspace_bytes(int P, int N, int Vz, int V);
+void *sorted_workspace_at(void *ws, int b0, int N, int Vz, int V);   // projections [b0, ...) of a batch
 
 // gather (+ pose adjoint).  g_grid may be NULL (pose-only adjoint), g_trpc may be NULL.
 int launch_gather_pose_bwd(const PoseArgs &a, const float *g_grid, const float *g_trpc,

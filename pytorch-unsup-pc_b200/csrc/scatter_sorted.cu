@@ -8,26 +8,56 @@
 //  1. sort_points_kernel (one CTA per projection): every point gets the key
 //     of its base grid row (iz*V + iy; out-of-frustum points get a sentinel)
 //     packed with its index as key<<16 | n, then a stable 4-pass LSD radix
-//     sort (4-bit digits) orders the points by row.  Each thread owns a
-//     contiguous chunk of the array and private digit counters, so the sort
-//     uses no atomics and equal keys keep ascending point index.
+//     sort (4-bit digits) orders the points by row -- in shared memory when the
+//     cloud fits (<= 12288 points).  Each thread owns a contiguous chunk of the
+//     array and private digit counters, so the sort uses no atomics and equal
+//     keys keep ascending point index.  The cell record of every point
+//     (ix + fp32 fractions) and the start of every row's segment are written
+//     once, here.
 //  2. segment_rows_kernel (one thread per output grid row): the row (z, y)
 //     receives contributions only from the four base rows (z-dz, y-dy); the
-//     thread walks those four sorted segments in a fixed order and sums into
-//     a private shared-memory row, which the CTA then stores coalesced.  Every
-//     voxel is written exactly once (no memset, no atomics) and its summation
-//     order is a pure function of the inputs.
+//     thread walks those four sorted segments in a fixed order -- segment
+//     bounds from the table, weights from the records: no pose, no search --
+//     and sums into a private shared-memory row, which the CTA then stores
+//     coalesced.  Every voxel is written exactly once (no memset, no atomics)
+//     and its summation order is a pure function of the inputs.
+// Round 2: records + shared-memory sort + segment table (workload C5's scatter
+// stage: 241 us -> see DESIGN.md section 5).
 #include "common.cuh"
 #include "pose.cuh"
 
 namespace dpc {
 
-constexpr int kSortThreads = 256;
+constexpr int kItemThreads = 256;        // sort_items_kernel: one thread per point
+constexpr int kSortThreads = 1024;       // sort_points_kernel: one CTA per projection
 constexpr int kRowThreads = 128;
+constexpr int kSmemSortMax = 12288;     // points per projection the shared-memory sort holds (2 x 48 KB)
 
+// Per projection: items A [N] | items B [N] | records [N] uint4 | sorted records [N] uint4 |
+// rowstart [Vz*V + 2], 16-byte aligned
+static size_t sorted_stride_bytes(int N, int Vz, int V) {
+  const size_t items = (((size_t)2 * N * sizeof(uint32_t)) + 15) & ~(size_t)15;
+  const size_t rows = (((size_t)(Vz * V + 2) * sizeof(uint32_t)) + 15) & ~(size_t)15;
+  return items + (size_t)2 * N * sizeof(uint4) + rows;
+}
 size_t sorted_workspace_bytes(int P, int N, int Vz, int V) {
-  (void)Vz; (void)V;
-  return (size_t)2 * P * N * sizeof(uint32_t);
+  return (size_t)P * sorted_stride_bytes(N, Vz, V);
+}
+struct SortedView {
+  uint32_t *A, *B;
+  uint4 *rec, *srec;       // records in point order / in sorted order
+  uint32_t *rowstart;
+};
+__host__ __device__ inline SortedView sorted_view(void *ws, size_t stride, int b, int N) {
+  char *base = (char *)ws + (size_t)b * stride;
+  const size_t items = (((size_t)2 * N * sizeof(uint32_t)) + 15) & ~(size_t)15;
+  SortedView v;
+  v.A = (uint32_t *)base;
+  v.B = v.A + N;
+  v.rec = (uint4 *)(base + items);
+  v.srec = v.rec + N;
+  v.rowstart = (uint32_t *)(v.srec + N);
+  return v;
 }
 
 struct PointSource {
@@ -61,21 +91,42 @@ __device__ __forceinline__ Cell point_cell(const PointSource &src, int b, int n,
   return make_cell(u0, u1, u2, Vz, V);
 }
 
+// One thread per point: the cell of every point is derived ONCE (fp64 pose, as everywhere) and
+// kept as a record {ix, rz, ry, rx} (fp32 fractions, as on the default path) next to its sort item
+// key << 16 | n (key = base grid row iz * V + iy; Vz * V for out-of-frustum points).
+__global__ void __launch_bounds__(kItemThreads)
+sort_items_kernel(PointSource src, float *__restrict__ tr_out, void *ws, size_t stride, int N,
+                  int Vz, int V) {
+  const int b = blockIdx.y, n = blockIdx.x * kItemThreads + threadIdx.x;
+  if (n >= N) return;
+  const SortedView sv = sorted_view(ws, stride, b, N);
+  const Cell c = point_cell(src, b, n, N, Vz, V, tr_out);
+  const uint32_t key = c.valid ? (uint32_t)(c.iz * V + c.iy) : (uint32_t)(Vz * V);
+  sv.A[n] = (key << 16) | (uint32_t)n;
+  sv.rec[n] = make_uint4((uint32_t)c.ix, __float_as_uint((float)c.rz), __float_as_uint((float)c.ry),
+                         __float_as_uint((float)c.rx));
+}
+
+// One CTA per projection: the items are sorted in SHARED memory when the cloud fits (SMEM; else in
+// the two global buffers), and the start of every grid row's segment is tabulated, so that the
+// last kernel neither recomputes a pose nor searches.
+template <bool SMEM>
 __global__ void __launch_bounds__(kSortThreads)
-sort_points_kernel(PointSource src, float *__restrict__ tr_out, uint32_t *__restrict__ bufA,
-                   uint32_t *__restrict__ bufB, int N, int Vz, int V) {
-  __shared__ uint32_t cnt[16 * kSortThreads];
+sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V) {
+  extern __shared__ uint32_t sm_sort[];           // cnt [16 * threads] | SMEM: A [N] | B [N]
   __shared__ uint32_t warp_tot[kSortThreads / 32];
+  uint32_t *cnt = sm_sort, *sm_items = sm_sort + 16 * kSortThreads;
   const int b = blockIdx.x, tid = threadIdx.x;
-  uint32_t *A = bufA + (size_t)b * N, *B = bufB + (size_t)b * N;
-  const uint32_t invalid_key = (uint32_t)(Vz * V);
-  for (int n = tid; n < N; n += kSortThreads) {
-    const Cell c = point_cell(src, b, n, N, Vz, V, tr_out);
-    const uint32_t key = c.valid ? (uint32_t)(c.iz * V + c.iy) : invalid_key;
-    A[n] = (key << 16) | (uint32_t)n;
-  }
+  const SortedView sv = sorted_view(ws, stride, b, N);
+  uint32_t *A = SMEM ? sm_items : sv.A, *B = SMEM ? sm_items + N : sv.B;
+  const uint32_t rows = (uint32_t)(Vz * V);       // the key of out-of-frustum points
+  if (SMEM)
+    for (int n = tid; n < N; n += kSortThreads) A[n] = sv.A[n];
   __syncthreads();
-  const int chunk = (N + kSortThreads - 1) / kSortThreads;
+  // contiguous chunk per thread (stable); an ODD chunk length keeps the threads' walks on
+  // different shared-memory banks
+  int chunk = (N + kSortThreads - 1) / kSortThreads;
+  chunk |= 1;
   const int lo = min(tid * chunk, N), hi = min(lo + chunk, N);
   uint32_t *from = A, *to = B;
   for (int pass = 0; pass < 4; ++pass) {
@@ -114,28 +165,27 @@ sort_points_kernel(PointSource src, float *__restrict__ tr_out, uint32_t *__rest
     __syncthreads();
     uint32_t *t = from; from = to; to = t;
   }
-  // 4 passes: the sorted array ends in bufA
-}
-
-__device__ __forceinline__ int lower_bound_key(const uint32_t *__restrict__ items, int N,
-                                               uint32_t key) {
-  int lo = 0, hi = N;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if ((items[mid] >> 16) < key) lo = mid + 1; else hi = mid;
+  // 4 passes: the sorted array ends in A.  Segment starts: rowstart[k] = first index whose key
+  // is >= k, for k = 0 .. rows + 1 (rowstart[rows] = the first out-of-frustum point,
+  // rowstart[rows + 1] = N); the sorted items go to the global buffer the second kernel reads
+  for (int i = tid; i < N; i += kSortThreads) {
+    const uint32_t item = A[i], key = item >> 16;
+    sv.srec[i] = sv.rec[item & 0xffffu];          // the records in sorted order: sequential reads later
+    const uint32_t prev = i > 0 ? (A[i - 1] >> 16) + 1u : 0u;
+    for (uint32_t k = prev; k <= key; ++k) sv.rowstart[k] = (uint32_t)i;
+    if (i == N - 1)
+      for (uint32_t k = key + 1; k <= rows + 1; ++k) sv.rowstart[k] = (uint32_t)N;
   }
-  return lo;
 }
 
 __global__ void __launch_bounds__(kRowThreads)
-segment_rows_kernel(PointSource src, const uint32_t *__restrict__ sorted, int N, int Vz, int V,
-                    float *__restrict__ grid) {
+segment_rows_kernel(const void *ws, size_t stride, int N, int Vz, int V, float *__restrict__ grid) {
   extern __shared__ float acc[];  // [V][kRowThreads + 1]
   constexpr int S = kRowThreads + 1;
   const int b = blockIdx.y, tid = threadIdx.x;
   const int rows = Vz * V;
   const int row = blockIdx.x * kRowThreads + tid;
-  const uint32_t *items = sorted + (size_t)b * N;
+  const SortedView sv = sorted_view(const_cast<void *>(ws), stride, b, N);
   for (int x = 0; x < V; ++x) acc[x * S + tid] = 0.f;
   if (row < rows) {
     const int oz = row / V, oy = row - oz * V;
@@ -145,14 +195,16 @@ segment_rows_kernel(PointSource src, const uint32_t *__restrict__ sorted, int N,
       for (int dy = 0; dy < 2; ++dy) {
         const int bz = oz - dz, by = oy - dy;
         if (bz < 0 || by < 0) continue;
-        const uint32_t key = (uint32_t)(bz * V + by);
-        const int i0 = lower_bound_key(items, N, key), i1 = lower_bound_key(items, N, key + 1);
+        const int key = bz * V + by;
+        const int i0 = (int)sv.rowstart[key], i1 = (int)sv.rowstart[key + 1];
         for (int i = i0; i < i1; ++i) {
-          const int n = (int)(items[i] & 0xffffu);
-          const Cell c = point_cell(src, b, n, N, Vz, V, nullptr);
-          const double wzy = (dz ? c.rz : 1.0 - c.rz) * (dy ? c.ry : 1.0 - c.ry);
-          acc[c.ix * S + tid] += (float)(wzy * (1.0 - c.rx));
-          if (c.ix + 1 < V) acc[(c.ix + 1) * S + tid] += (float)(wzy * c.rx);
+          const uint4 r = sv.srec[i];
+          const int ix = (int)r.x;
+          const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
+          // the same fp32 weight products as the default plane scatter (blur_xy.cu)
+          const float wzy = (dz ? rz : 1.f - rz) * (dy ? ry : 1.f - ry);
+          acc[ix * S + tid] += wzy * (1.f - rx);
+          if (ix + 1 < V) acc[(ix + 1) * S + tid] += wzy * rx;
         }
       }
   }
@@ -186,8 +238,23 @@ int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N
     src.pose.points = nullptr;
     src.tr_pc = tr_pc_in;
   }
-  uint32_t *bufA = (uint32_t *)ws, *bufB = bufA + (size_t)P * N;
-  sort_points_kernel<<<P, kSortThreads, 0, s>>>(src, a ? tr_pc_out : nullptr, bufA, bufB, N, Vz, V);
+  const size_t stride = sorted_stride_bytes(N, Vz, V);
+  sort_items_kernel<<<dim3((N + kItemThreads - 1) / kItemThreads, P), kItemThreads, 0, s>>>(
+      src, a ? tr_pc_out : nullptr, ws, stride, N, Vz, V);
+  if (int e = check_launch("sort_items")) return e;
+  const size_t cnt_smem = (size_t)16 * kSortThreads * sizeof(uint32_t);
+  static DeviceOnce sort_once;
+  if (sort_once.first()) {
+    cudaFuncSetAttribute(sort_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)cnt_smem + 2 * kSmemSortMax * (int)sizeof(uint32_t));
+    cudaFuncSetAttribute(sort_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)cnt_smem);
+  }
+  if (N <= kSmemSortMax)
+    sort_points_kernel<true><<<P, kSortThreads, cnt_smem + (size_t)2 * N * sizeof(uint32_t), s>>>(
+        ws, stride, N, Vz, V);
+  else
+    sort_points_kernel<false><<<P, kSortThreads, cnt_smem, s>>>(ws, stride, N, Vz, V);
   if (int e = check_launch("sort_points")) return e;
   const size_t smem = (size_t)V * (kRowThreads + 1) * sizeof(float);
   static DeviceOnce attr_once;
@@ -196,8 +263,13 @@ int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N
                          128 * (kRowThreads + 1) * (int)sizeof(float));
   }
   dim3 g((Vz * V + kRowThreads - 1) / kRowThreads, P);
-  segment_rows_kernel<<<g, kRowThreads, smem, s>>>(src, bufA, N, Vz, V, grid);
+  segment_rows_kernel<<<g, kRowThreads, smem, s>>>(ws, stride, N, Vz, V, grid);
   return check_launch("segment_rows");
+}
+
+// the workspace of projections [b0, ...) inside a whole-batch workspace
+void *sorted_workspace_at(void *ws, int b0, int N, int Vz, int V) {
+  return (char *)ws + (size_t)b0 * sorted_stride_bytes(N, Vz, V);
 }
 
 }  // namespace dpc

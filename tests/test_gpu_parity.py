@@ -308,3 +308,40 @@ def test_plane_local_path_matches_global_grid_path(dpc, V, N, sigma, kind):
     assert torch.equal(out_p["tr_pc"], out_g["tr_pc"])
     for k in grads_p:
         assert _golden.rel_err(grads_p[k], grads_g[k]) < GRAD_TOL, k
+
+
+def test_release_and_recreate_internal_streams(dpc):
+    """dpc_release() destroys the calling thread's internal side streams / events (the only state
+    the library keeps); the next batch of >= 64 projections re-creates them and gives the same bits."""
+    import ctypes
+    from pytorch_unsup_pc_b200 import _lib, ops
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    cfg = default_cfg(vox_size=32, pc_gauss_kernel_size=11)
+    P, N = 64, 500
+    case = _inputs.make_case(cfg, P, N, 77, scale=True, screened=False)
+    taps = ops.host_taps(CF.smoothing_taps(cfg, 1.5))
+    params = ops.make_params(cfg, P, N, flip_y=True)
+    d = {k: case[k].to(dev).contiguous() for k in ("points", "quat", "scale")}
+    f32 = dict(dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.dpc_workspace_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev)
+    cells = torch.empty(lib.dpc_cells_bytes(ctypes.byref(params)), dtype=torch.uint8, device=dev)
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def forward():
+        grid, bits = torch.empty(P, 32, 32, 32, **f32), torch.empty(P, 32, 32, 1, dtype=torch.int32, device=dev)
+        mask, depth, tr = torch.empty(P, 32, 32, **f32), torch.empty(P, 32, 32, **f32), torch.empty(P, N, 3, **f32)
+        _lib.check(lib.dpc_project_fwd(ctypes.byref(params), d["points"].data_ptr(), d["quat"].data_ptr(),
+                                       None, None, d["scale"].data_ptr(), *ops._tap_args(taps), 0,
+                                       tr.data_ptr(), grid.data_ptr(), bits.data_ptr(), cells.data_ptr(),
+                                       mask.data_ptr(), depth.data_ptr(), None, None, ws.data_ptr(),
+                                       ws.numel(), sp), "fwd")
+        torch.cuda.synchronize(dev)
+        return mask, depth, tr
+    assert lib.dpc_project_chunks(ctypes.byref(params)) == 2
+    a = forward()
+    assert lib.dpc_release() == 0
+    assert lib.dpc_release() == 0            # nothing left to release: still fine
+    b = forward()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
