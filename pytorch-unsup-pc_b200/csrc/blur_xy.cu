@@ -89,6 +89,11 @@ __device__ __forceinline__ u64 bx_pack2(float lo, float hi) {
 __device__ __forceinline__ void bx_unpack2(u64 v, float &lo, float &hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ u64 bx_add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ u64 bx_fma2(u64 a, u64 b, u64 c) {
   u64 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -128,7 +133,7 @@ struct XYCfg {
 // 16 packed outputs from a window of W pair-positions starting at `win`
 // IN: how a window element becomes the value to blur: 0 as stored; 1 clamp(raw, 0, 1) of a
 // non-negative raw value = min(v, 1); 2 the plane scatter's biased fixed point (see
-// scatter_add_fixed): the tile holds 1 + raw, so clamp(raw, 0, 1) = min(v, 2) - 1, exactly
+// scatter_add_fixed): the tile holds 1 + min(raw, 1), so clamp(raw, 0, 1) = v - 1, exactly
 // SKIP_LO / SKIP_HI: the first / last so many window positions are known to be zero padding (the
 // block at the start / end of a line): their loads and their FFMA2 are left out.
 template <int R, int J, int W2, int IN = 0, int SKIP_LO = 0, int SKIP_HI = 0>
@@ -145,13 +150,15 @@ __device__ __forceinline__ void window_fma2(const float2 *__restrict__ win, cons
       v4.y = fminf(v4.y, 1.f);
       v4.z = fminf(v4.z, 1.f);
       v4.w = fminf(v4.w, 1.f);
-    } else if (IN == 2) {
-      v4.x = fminf(v4.x, 2.f) - 1.f;
-      v4.y = fminf(v4.y, 2.f) - 1.f;
-      v4.z = fminf(v4.z, 2.f) - 1.f;
-      v4.w = fminf(v4.w, 2.f) - 1.f;
     }
-    const u64 vv[2] = {bx_pack2(v4.x, v4.y), bx_pack2(v4.z, v4.w)};
+    u64 vv[2] = {bx_pack2(v4.x, v4.y), bx_pack2(v4.z, v4.w)};
+    if (IN == 2) {
+      // the scatter caps an element at exactly 2.0 (scatter_add_fixed), so min(v, 2) is v itself
+      // and clamp(raw, 0, 1) = v - 1: one packed add per pair, no FMNMX
+      const u64 m1 = bx_pack2(-1.f, -1.f);
+      vv[0] = bx_add2(vv[0], m1);
+      vv[1] = bx_add2(vv[1], m1);
+    }
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -247,10 +254,11 @@ __device__ __forceinline__ float smem_add_new(float *p, float w) {
 // the order in which points arrive, so the default path is bit-reproducible run to run.
 // raw > 1  <=>  bits > bits(2.0f) (positive floats order like their bit patterns); elements that
 // are already past 2.0 are left alone, and every add that lands past 2.0 is followed by an
-// atomicMin back to the first pattern above it: the check and the add are two operations, so a
-// pile of threads may all pass the check and add on top of each other, but the element ENDS at a
-// pattern in (2.0, 2.0 + 2^-22] whatever the interleaving (decoded as raw > 1 -> clamp gives 1),
-// never in the Inf/NaN or sign-bit range.  (The transient sum wraps 2^32 only past 384 in-flight
+// atomicMin back to EXACTLY 2.0: the check and the add are two operations, so a pile of threads
+// may all pass the check and add on top of each other, but the element ENDS at 2.0 whatever the
+// interleaving -- never in the Inf/NaN or sign-bit range -- and 2.0 decodes as clamp(raw, 0, 1) = 1
+// without a min on the load (the raw <= 1 bit was cleared by the add that crossed 2.0; an element
+// that reaches 2.0 without crossing it has raw == 1 and keeps its bit).  (The transient sum wraps 2^32 only past 384 in-flight
 // adds of weight 1 to one element -- more than three quarters of the largest CTA.)
 constexpr uint32_t kFixOne = 0x3F800000u, kFixTwo = 0x40000000u;
 __device__ __forceinline__ bool scatter_add_fixed(float *p, float w) {   // true: element now > 1
@@ -258,7 +266,7 @@ __device__ __forceinline__ bool scatter_add_fixed(float *p, float w) {   // true
   if (*reinterpret_cast<volatile uint32_t *>(ip) > kFixTwo) return false;   // saturated before
   const uint32_t wq = __float2uint_rn(w * 8388608.f);
   if (atomicAdd(ip, wq) + wq <= kFixTwo) return false;
-  atomicMin(ip, kFixTwo + 1u);
+  atomicMin(ip, kFixTwo);
   return true;
 }
 

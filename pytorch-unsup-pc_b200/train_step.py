@@ -259,5 +259,9 @@ def bench(env, args):
             "exposed_ms": max(0.0, (ms - ms_ns) / steps),
             "overlapped_fraction": max(0.0, min(1.0, 1.0 - (ms - ms_ns) / max(ms_ar, 1e-9)))}
     del batches
+    # (graphs that hold captured NCCL work are gone by now: dist.destroy_process_group() does not
+    # return while one is alive)
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return rec
