@@ -401,7 +401,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #endif
       __syncthreads();
       for (int i = tid; i < C::RH * V / 32; i += C::THREADS)
-        bits_out[plane * (V * V / 32) + h * (C::RH * V / 32) + i] = sbits[i];
+        st_stream(bits_out + plane * (V * V / 32) + h * (C::RH * V / 32) + i, sbits[i]);   // next read: the backward
       // clamp(raw, 0, 1) happens in the X pass, on the window loads
     }
     // ---- stage rows [h*RH, (h+1)*RH) as row pairs (r, r + RH/2) ----
@@ -413,8 +413,12 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #ifdef DPC_PROBE_NO_FILL
       float4 a = make_float4(0.f, 1.f, 0.f, 1.f), b = a;
 #else
-      float4 a = ld_dep(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
-      float4 b = ld_dep(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
+      // (coherent like ld_dep -- the programmatic primary wrote the plane -- and evict-first: for
+      // the plane-gather backward this is the gradient grid's last reader)
+      float4 a = (POINTS && MASK_OUT) ? ld_stream(reinterpret_cast<const float4 *>(sp + r0 * V) + c4)
+                                      : ld_dep(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
+      float4 b = (POINTS && MASK_OUT) ? ld_stream(reinterpret_cast<const float4 *>(sp + r1 * V) + c4)
+                                      : ld_dep(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
 #endif
       if (WRITE_BITS) {
         uint32_t na = le1_nibble(a) << (4 * (tid & 7)), nb = le1_nibble(b) << (4 * (tid & 7));

@@ -103,6 +103,19 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 #endif
 template <typename T>
 __device__ __forceinline__ T ld_dep(const T *p) { return DPC_LD_DEP_NC ? __ldg(p) : __ldcg(p); }
+// Cache hints (A/B: -DDPC_CACHE_HINTS=0).  Stores of data nobody re-reads within the pass (the
+// saved ray state, tr_pc, the point gradients) and loads of data read exactly once are marked
+// streaming (evict-first), so that the producer -> consumer grids of the chain (XY-blurred grid,
+// gradient grid: 32 MiB per half-batch each) keep their L2 lines.
+#ifndef DPC_CACHE_HINTS
+#define DPC_CACHE_HINTS 1
+#endif
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v) {
+  if (DPC_CACHE_HINTS) __stcs(p, v); else *p = v;
+}
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T *p) { return DPC_CACHE_HINTS ? __ldcs(p) : *p; }
 #ifndef DPC_PDL_EARLY
 #define DPC_PDL_EARLY 0
 #endif

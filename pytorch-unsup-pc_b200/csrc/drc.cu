@@ -225,7 +225,7 @@ __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int 
           load_ok ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
       const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
       const u64 keep2 = sink(j, z, b2);      // what the backward wants to find in this voxel pair
-      if (SAVE) *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = keep2;
+      if (SAVE) st_stream(reinterpret_cast<u64 *>(bs + (size_t)j * VV), keep2);   // next read: the backward
     }
   };
   if (VZ) {
@@ -288,7 +288,7 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   stream_blur_z2<V, R, SAVE, VZ>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
                                  [&](int j, int z, u64 b2) -> u64 {
     if (FAST && j == 0 && z > 0) {   // block start: checkpoint the transmittance
-      *ckp = T2;
+      st_stream(ckp, T2);            // next read: the backward
       ckp += VV / 2;
     }
     const float psi = fmaf(kf, c.inv_z, c.depth0);

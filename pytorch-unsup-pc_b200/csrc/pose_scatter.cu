@@ -286,9 +286,9 @@ pose_bin_kernel(PoseArgs a, float *__restrict__ tr_pc, CellsView cells) {
       const PosePoint pp = pose_point(q, a.points[si], a.points[si + 1], a.points[si + 2], has_t,
                                       t0, t1, t2, f, a.cam_dist);
       if (WRITE_TRPC) {
-        tr_pc[pi] = (float)pp.u0;
-        tr_pc[pi + 1] = (float)pp.u1;
-        tr_pc[pi + 2] = (float)pp.u2;
+        st_stream(tr_pc + pi, (float)pp.u0);
+        st_stream(tr_pc + pi + 1, (float)pp.u1);
+        st_stream(tr_pc + pi + 2, (float)pp.u2);
       }
       const Cell c = make_cell(pp.u0, pp.u1, pp.u2, a.Vz, a.V);
       if (c.valid) {
@@ -566,7 +566,7 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
       // SELECTED afterwards: an unwritten slot may hold anything, NaN included)
       const size_t idx = (size_t)bj * a.N + n;
       const unsigned iz = cells.cellz[(size_t)b * cells.Npad + n];
-      const float4 s0 = ld_dep(part + idx), s1 = ld_dep(part + (size_t)a.P * a.N + idx);
+      const float4 s0 = ld_stream(part + idx), s1 = ld_stream(part + (size_t)a.P * a.N + idx);   // last reader
       const bool in0 = iz != kCellNone, in1 = in0 && (int)iz + 1 < a.Vz;
       float gu0 = ((in0 ? s0.x : 0.f) + (in1 ? s1.x : 0.f)) * (float)(a.Vz - 1);
       float gu1 = ((in0 ? s0.y : 0.f) + (in1 ? s1.y : 0.f)) * (float)(a.V - 1);
@@ -585,9 +585,9 @@ gather_pose_bwd_kernel(PoseArgs a, const float *__restrict__ g_grid,
       const float vp = vx * p0 + vy * p1 + vz * p2;
       const float gp = g0 * p0 + g1 * p1 + g2 * p2;
       const float c0 = vy * g2 - vz * g1, c1 = vz * g0 - vx * g2, c2 = vx * g1 - vy * g0;   // v x g
-      g_points[pi] = ww * g0 + 2.f * vg * vx - 2.f * w * c0;
-      g_points[pi + 1] = ww * g1 + 2.f * vg * vy - 2.f * w * c1;
-      g_points[pi + 2] = ww * g2 + 2.f * vg * vz - 2.f * w * c2;
+      st_stream(g_points + pi, ww * g0 + 2.f * vg * vx - 2.f * w * c0);
+      st_stream(g_points + pi + 1, ww * g1 + 2.f * vg * vy - 2.f * w * c1);
+      st_stream(g_points + pi + 2, ww * g2 + 2.f * vg * vz - 2.f * w * c2);
       const float x0 = p1 * g2 - p2 * g1, x1 = p2 * g0 - p0 * g2, x2 = p0 * g1 - p1 * g0;   // p x g
       fa[0] += 2.f * w * gp + 2.f * (vx * x0 + vy * x1 + vz * x2);
       fa[1] += -2.f * gp * vx + 2.f * (vg * p0 + vp * g0) + 2.f * w * x0;

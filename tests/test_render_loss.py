@@ -164,3 +164,57 @@ def test_large_batches_two_half_chains(B, views, C, N, V, keep):
     assert abs(out["loss"].item() - total.item()) <= 2e-6 * abs(total.item())
     for k, a, b in zip(("points", "quat", "scale"), grads, cgrads):
         assert torch.equal(a, b), (k, (a - b).abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("keep", [1.0, 0.5])
+def test_all_optional_inputs_against_oracle_composition(keep):
+    """Translation, per-projection focal length, occupancy scale, per-view weights, dropout and a
+    non-unit weight_scale together, on screened inputs: the fused op against the oracle
+    composition (oracle.replicas + closed_form + loss, fp64) -- loss / projections 1e-5,
+    every gradient 1e-4, argmin equal."""
+    import pytorch_unsup_pc_b200 as dpc
+    import _inputs
+    from oracle import closed_form as CF
+    from oracle.replicas import tf_repeat_0
+    dev = torch.device("cuda:0")
+    B, views, C, N, V, G = 3, 2, 3, 900, 32, 64
+    R, P, BV = views * C, B * views * C, B * views
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=11, pose_predict_num_candidates=C,
+                      variable_num_views=True)
+    case = _inputs.make_case(cfg, P, N, 3100 + int(10 * keep), translation=True, focal=True,
+                             scale=True, screened=False)
+    g = torch.Generator().manual_seed(91)
+    pts = case["points"][:B].contiguous()
+    for _ in range(50):         # screen every cloud against all of its replicas' poses
+        tr = CF.pose_transform(cfg, tf_repeat_0(pts, R), case["quat"], case["translation"], case["focal"])
+        bad = _inputs.near_boundary(cfg, tr).reshape(B, R, -1).any(dim=1)
+        if int(bad.sum()) == 0:
+            break
+        pts[bad] = (torch.rand(int(bad.sum()), 3, generator=g) - 0.5) * 0.9
+    masks = (torch.rand(BV, 1, G, G, generator=g) > 0.55).float()
+    weights = (torch.rand(BV, generator=g) > 0.3).float() + 0.25
+    kernel = CF.smoothing_taps(cfg, 1.2)
+    idx = None
+    if keep < 1:
+        M = int(N * keep)
+        idx = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(P)])
+    names = ("points", "quat", "translation", "focal", "scale")
+    cpu = dict(points=pts, quat=case["quat"], translation=case["translation"], focal=case["focal"],
+               scale=case["scale"])
+    lo = {k: v.clone().requires_grad_() for k, v in cpu.items()}
+    loss_o, min_o, proj_o = ORL.project_candidates_loss(
+        cfg, lo["points"], lo["quat"], masks, C, kernel, lo["scale"], lo["translation"], lo["focal"],
+        weight_scale=0.7, valid_samples=weights, indices=None if idx is None else _pairs(idx))
+    g_o = torch.autograd.grad(loss_o, [lo[k] for k in names])
+    lc = {k: v.to(dev).requires_grad_() for k, v in cpu.items()}
+    out = dpc.project_candidates_loss(cfg, lc["points"], lc["quat"], lc["translation"], masks.to(dev),
+                                      kernel, scaling_factor=lc["scale"], focal_length=lc["focal"],
+                                      weight_scale=0.7, valid_samples=weights.to(dev),
+                                      indices=None if idx is None else idx.to(dev))
+    g_c = torch.autograd.grad(out["loss"], [lc[k] for k in names])
+    assert out["min_loss"].tolist() == min_o.tolist()
+    assert abs(out["loss"].item() - loss_o.item()) <= 1e-5 * abs(loss_o.item())
+    assert _golden.rel_err(out["projs"], proj_o.float()) < 1e-5
+    for k, a, b in zip(names, g_c, g_o):
+        assert _golden.rel_err(a, b.reshape(a.shape)) < 1e-4, k
