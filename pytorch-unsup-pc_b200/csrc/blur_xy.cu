@@ -415,9 +415,12 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #else
       // (coherent like ld_dep -- the programmatic primary wrote the plane -- and evict-first: for
       // the plane-gather backward this is the gradient grid's last reader)
-      float4 a = (POINTS && MASK_OUT) ? ld_stream(reinterpret_cast<const float4 *>(sp + r0 * V) + c4)
+#ifndef DPC_FILL_STREAM
+#define DPC_FILL_STREAM 1
+#endif
+      float4 a = (POINTS && MASK_OUT && DPC_FILL_STREAM) ? ld_stream(reinterpret_cast<const float4 *>(sp + r0 * V) + c4)
                                       : ld_dep(reinterpret_cast<const float4 *>(sp + r0 * V) + c4);
-      float4 b = (POINTS && MASK_OUT) ? ld_stream(reinterpret_cast<const float4 *>(sp + r1 * V) + c4)
+      float4 b = (POINTS && MASK_OUT && DPC_FILL_STREAM) ? ld_stream(reinterpret_cast<const float4 *>(sp + r1 * V) + c4)
                                       : ld_dep(reinterpret_cast<const float4 *>(sp + r1 * V) + c4);
 #endif
       if (WRITE_BITS) {

@@ -511,6 +511,34 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// The same copy with an L2 evict-first policy: the saved ray state is read exactly once, and at
+// 32 MiB per half-batch it otherwise pushes the gradient grid this kernel WRITES out of L2 before
+// the plane kernel reads it (ncu, steady state: the plane kernel read 37 MB per launch from DRAM).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#ifndef DPC_GGRID_KEEP
+#define DPC_GGRID_KEEP 0       // A/B: gradient-grid stores with an L2 evict-last policy
+#endif
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep(u64 *p, u64 v, uint64_t pol) {
+  if (DPC_GGRID_KEEP)
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+  else
+    *p = v;
+}
+__device__ __forceinline__ void bulk_g2s_once(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                              uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -571,12 +599,18 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
     // rows issued by the 32 lanes of warp 0, deepest rows first (measured: 35.2 us; all 64 rows
     // from one thread: 37.7 us -- the last rows are issued too late)
     const float *row0 = vgrid + (col0 - (size_t)(2 * tid));     // the CTA's first pair (tid == lane here)
-    for (int z = VZ - 1 - tid; z >= 0; z -= 32)
-      bulk_g2s(tile + (size_t)z * kBwdThreads, row0 + (size_t)z * VV, ROW_BYTES, bars + z / L);
+    const uint64_t once = l2_evict_first_policy();
+    for (int z = VZ - 1 - tid; z >= 0; z -= 32) {
+      if (DPC_CACHE_HINTS)
+        bulk_g2s_once(tile + (size_t)z * kBwdThreads, row0 + (size_t)z * VV, ROW_BYTES, bars + z / L, once);
+      else
+        bulk_g2s(tile + (size_t)z * kBwdThreads, row0 + (size_t)z * VV, ROW_BYTES, bars + z / L);
+    }
   }
   const float s = c.has_scale ? __ldg(scale + b) : 1.f;
   const u64 s2 = pack2(s, s), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
   const u64 ec2 = pack2(c.exp_clip, c.exp_clip);
+  const uint64_t keep_pol = DPC_GGRID_KEEP ? l2_evict_last_policy() : 0ull;
   // transmittance at the block starts (block 0 starts at 1)
   u64 tstart[NBLK];
   tstart[0] = one2;
@@ -648,7 +682,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
 #ifdef DPC_PROBE_NO_STORE
         ds2 = add2(ds2, ring_dot2<R, L>(ring, k2, j, true));     // timing probe: no g_grid store
 #else
-        *reinterpret_cast<u64 *>(gout + (size_t)j * VV) = ring_dot2<R, L>(ring, k2, j, true);
+        st_keep(reinterpret_cast<u64 *>(gout + (size_t)j * VV), ring_dot2<R, L>(ring, k2, j, true), keep_pol);
 #endif
       }
     }
@@ -672,7 +706,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
     for (int j = L - 1; j >= L - R; --j) {
       ring[j] = 0;
       const int z = j - L + R;
-      if (z < VZ) *reinterpret_cast<u64 *>(gout + (size_t)z * VV) = ring_dot2<R, L>(ring, k2, j, true);
+      if (z < VZ) st_keep(reinterpret_cast<u64 *>(gout + (size_t)z * VV), ring_dot2<R, L>(ring, k2, j, true), keep_pol);
     }
   }
   if (scale_partials) {
