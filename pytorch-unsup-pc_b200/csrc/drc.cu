@@ -225,7 +225,12 @@ __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int 
           load_ok ? *reinterpret_cast<const u64 *>(col + (size_t)(j + AHEAD) * VV) : 0ull;
       const u64 b2 = ring_dot2<R, L>(ring, k2, (j + L - R) % L, false);
       const u64 keep2 = sink(j, z, b2);      // what the backward wants to find in this voxel pair
-      if (SAVE) st_stream(reinterpret_cast<u64 *>(bs + (size_t)j * VV), keep2);   // next read: the backward
+      // next read: the backward.  Streaming only where a half-batch of grids can live in L2
+      // (64^3: 32 MiB); at 128^3 (512 MiB) the hint costs 10 us per launch and keeps nothing
+      if (SAVE) {
+        if (V <= 64) st_stream(reinterpret_cast<u64 *>(bs + (size_t)j * VV), keep2);
+        else *reinterpret_cast<u64 *>(bs + (size_t)j * VV) = keep2;
+      }
     }
   };
   if (VZ) {
@@ -288,7 +293,7 @@ blurz_drc_fwd_kernel(const float *grid, const float *__restrict__ scale, RayCons
   stream_blur_z2<V, R, SAVE, VZ>(grid + col0, SAVE ? bsave + col0 : nullptr, c.Vz, kz,
                                  [&](int j, int z, u64 b2) -> u64 {
     if (FAST && j == 0 && z > 0) {   // block start: checkpoint the transmittance
-      st_stream(ckp, T2);            // next read: the backward
+      if (V <= 64) st_stream(ckp, T2); else *ckp = T2;      // next read: the backward
       ckp += VV / 2;
     }
     const float psi = fmaf(kf, c.inv_z, c.depth0);
@@ -601,7 +606,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
     const float *row0 = vgrid + (col0 - (size_t)(2 * tid));     // the CTA's first pair (tid == lane here)
     const uint64_t once = l2_evict_first_policy();
     for (int z = VZ - 1 - tid; z >= 0; z -= 32) {
-      if (DPC_CACHE_HINTS)
+      if (DPC_CACHE_HINTS && V <= 64)
         bulk_g2s_once(tile + (size_t)z * kBwdThreads, row0 + (size_t)z * VV, ROW_BYTES, bars + z / L, once);
       else
         bulk_g2s(tile + (size_t)z * kBwdThreads, row0 + (size_t)z * VV, ROW_BYTES, bars + z / L);
