@@ -414,7 +414,20 @@ static int chunk_size(const dpc_params *p) {
   // pose adjoint: ~25 % of the step, a few hundred CTAs each) of one half overlap the FMA-bound
   // grid kernels of the other.  Measured at workload A: 148.0 vs 153.6 us per step; quarters
   // lose (177.5 us: too few CTAs per kernel).
-  if (p->P >= 64 && p->P % 2 == 0) return p->P / 2;
+  // Larger batches at 64^3 and below: chunks of at most 64 MiB of grid (64 projections at 64^3), so
+  // that a chunk's producer -> consumer grids stay in L2 (config-3 shapes, 256 projections:
+  // 522.5 us per step as two halves of 128, 511.9 as four chunks of 64, 518.1 as eight of 32).
+  // At 128^3 a projection is 8 MiB and smaller chunks only lose (workload B: 2004 us as halves of
+  // 64, 2021 / 2059 / 2179 us as chunks of 16 / 8 / 4).
+  if (p->P >= 64 && p->P % 2 == 0) {
+    int chunk = p->P / 2;
+    if (p->V <= 64) {
+      const long long per = (long long)p->Vz * p->V * p->V * 4;
+      const int cap = (int)((64ll << 20) / per);
+      if (cap >= 32 && chunk > cap) chunk = cap;
+    }
+    return chunk;
+  }
   return p->P;
 }
 
