@@ -112,11 +112,21 @@ def stage_fma(V, Vz, K):
 # DRAM bytes per whole-batch launch (dram__bytes_read.sum + dram__bytes_write.sum) of each stage's
 # kernel(s) at workload A, from the committed `ncu --set full` capture NCU_CAPTURE (cold L2: ncu
 # flushes the caches before every replay).  None = not captured for that workload.
-NCU_CAPTURE = "profiles/r01_ncu_full_step_pdl.csv"
+NCU_CAPTURE = "profiles/r02_ncu_full_step.csv"
 NCU_TRAFFIC_BYTES = {
-    "A": {"pose_scatter": 6.18e6 + 0.0, "blur_xy_fwd": 7.47e6 + 11.24e6,
-          "blurz_drc_fwd": 67.15e6 + 12.97e6, "drc_blurz_bwd": 71.36e6 + 23.46e6,
-          "blur_xy_bwd": 77.02e6 + 3.43e6, "gather_pose_bwd": 23.12e6 + 0.0},
+    "A": {"pose_scatter": 6.18e6 + 0.0, "blur_xy_fwd": 7.47e6 + 14.14e6,
+          "blurz_drc_fwd": 67.15e6 + 13.71e6, "drc_blurz_bwd": 71.36e6 + 11.37e6,
+          "blur_xy_bwd": 77.26e6 + 4.60e6, "gather_pose_bwd": 23.12e6 + 0.0},
+}
+# The same from a capture WITHOUT cache flushes of the replayed CUDA graph (`ncu --cache-control
+# none --graph-profiling node`, scripts/profile_graph.py; profiles/r02_ncu_steady_state_graph_replay
+# .csv): DRAM read + write per HALF-batch launch with L2 as the previous kernels of the chain left
+# it (ncu still serialises the two half-batch chains).  x 2 = per whole batch.
+NCU_STEADY_CAPTURE = "profiles/r02_ncu_steady_state_graph_replay.csv"
+NCU_STEADY_BYTES_HALF = {
+    "A": {"pose_scatter": 1.41e6 + 0.13e6, "blur_xy_fwd": 3.76e6 + 1.73e6,
+          "blurz_drc_fwd": 0.50e6 + 2.05e6, "drc_blurz_bwd": 35.64e6 + 4.32e6,
+          "blur_xy_bwd": 37.31e6 + 0.0, "gather_pose_bwd": 8.72e6 + 0.0},
 }
 
 
@@ -712,6 +722,7 @@ def bench_projection(env, key, full):
     peak, peak_src = env.hbm_peak
     step_frac = (value / world) * algorithmic_bytes(N, V, Vz) / 1e9 / peak
     traffic = None if (args.global_grid or deterministic) else NCU_TRAFFIC_BYTES.get(key, {}).get(top)
+    steady = None if (args.global_grid or deterministic) else NCU_STEADY_BYTES_HALF.get(key, {}).get(top)
     fma_peak = env.fma_peak
     fp32 = None
     if fma_peak:
@@ -785,6 +796,10 @@ def bench_projection(env, key, full):
                      # HBM peak: its ceilings are shared-memory bandwidth and FP32 FMA issue
                      "traffic_gbs": None if traffic is None else traffic / (stages[top] * 1e-3) / 1e9,
                      "dram_frac_cold": None if traffic is None else traffic / (stages[top] * 1e-3) / 1e9 / peak,
+                     # steady state: no cache flush, replayed graph (2 x the half-batch launch)
+                     "dram_frac_steady": None if steady is None else 2 * steady / (stages[top] * 1e-3) / 1e9 / peak,
+                     "traffic_steady": None if steady is None else 2 * steady,
+                     "traffic_steady_source": NCU_STEADY_CAPTURE,
                      "fp32_frac": None if fp32 is None else fp32["kernel_frac"],
                      "fp32": fp32,
                      "limiter": "shared-memory bandwidth / FP32 FMA issue, not HBM"},

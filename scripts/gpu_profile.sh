@@ -14,3 +14,9 @@ DPC_CHUNK=100000 python scripts/profile_step.py --steps 2 > gpurun_out/plain_$ta
 DPC_CHUNK=100000 timeout 600 ncu --set full --clock-control none --import-source on -f \
     -o gpurun_out/prof_$tag python scripts/profile_step.py --steps 2 > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full capture rc=$?"; ls -la gpurun_out/prof_$tag.ncu-rep
+# summaries are made here: the report itself may exceed what gpurun copies back (64 MiB in all)
+python scripts/ncu_summary.py gpurun_out/prof_$tag.ncu-rep > gpurun_out/ncu_full_$tag.csv 2>/dev/null
+ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/ncu_raw_$tag.csv 2>/dev/null
+python scripts/ncu_sass_mix.py gpurun_out/prof_$tag.ncu-rep > gpurun_out/sass_mix_$tag.txt 2>/dev/null
+rm -f gpurun_out/prof_$tag.ncu-rep
+ls -la gpurun_out/ | tail -8
