@@ -234,6 +234,23 @@ __device__ __forceinline__ void for_each_touching_point(const TouchRange &t, int
   if (i < t.hi) f(first, i < t.mid ? 1 : 0);
   for (i += nthreads; i < t.hi; i += nthreads) f(ld_dep(t.srec + i), i < t.mid ? 1 : 0);
 }
+// ... with the thread's SECOND record prefetched as well (DPC_XY_PREFETCH2: a plane of workload A
+// is touched by ~250 points, two per thread of a 128-thread CTA)
+template <typename F>
+__device__ __forceinline__ void for_each_touching_point2(const TouchRange &t, int tid, int nthreads,
+                                                         const uint4 first, const uint4 second, F &&f) {
+  uint32_t i = t.lo + tid;
+  if (i < t.hi) f(first, i < t.mid ? 1 : 0);
+  i += nthreads;
+  if (i < t.hi) f(second, i < t.mid ? 1 : 0);
+  for (i += nthreads; i < t.hi; i += nthreads) f(ld_dep(t.srec + i), i < t.mid ? 1 : 0);
+}
+__device__ __forceinline__ uint4 second_touching_record(const TouchRange &t, int tid, int nthreads) {
+  return t.lo + tid + nthreads < t.hi ? ld_dep(t.srec + t.lo + tid + nthreads) : make_uint4(0u, 0u, 0u, 0u);
+}
+#ifndef DPC_XY_PREFETCH2
+#define DPC_XY_PREFETCH2 1     // forward plane scatter: prefetch two records per thread at kernel entry
+#endif
 __device__ __forceinline__ uint4 first_touching_record(const TouchRange &t, int tid) {
   return t.lo + tid < t.hi ? ld_dep(t.srec + t.lo + tid) : make_uint4(0u, 0u, 0u, 0u);
 }
@@ -312,10 +329,17 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   const int pb = SLOTS ? __ldg(bmap + pj) : pj;
   const size_t bplane = SLOTS ? (size_t)pb * Vz + pz : plane;       // plane index of the clamp bits
   TouchRange touch = {0u, 0u, 0u, nullptr};
-  uint4 rec0 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 rec0 = make_uint4(0u, 0u, 0u, 0u), rec1 = rec0;
+#ifndef DPC_XY_PREFETCH2_BWD
+#define DPC_XY_PREFETCH2_BWD 0   // measured: no difference in the backward gather (39.7 vs 39.8 us)
+#endif
+  // (not with SLOTS: the slot / plane index pair leaves no room for four more registers)
+  constexpr bool PRE2 = POINTS && (WRITE_BITS || (DPC_XY_PREFETCH2_BWD && !SLOTS)) && DPC_XY_PREFETCH &&
+                        DPC_XY_PREFETCH2;
   if (POINTS && DPC_XY_PREFETCH) {
     touch = touch_range(cells, pb, pz, N);
     rec0 = first_touching_record(touch, tid);
+    if (PRE2) rec1 = second_touching_record(touch, tid, C::THREADS);
   }
   // A plane no point touches (real clouds fill a fraction of the frustum's depth): forward, its
   // raw occupancy is zero, so both blur passes give zero and every raw <= 1 bit is set; backward,
@@ -387,7 +411,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
         touch = touch_range(cells, pb, pz, N);
         rec0 = first_touching_record(touch, tid);
       }
-      for_each_touching_point(touch, tid, C::THREADS, rec0, [&](const uint4 r, int dz) {
+      auto scatter_point = [&](const uint4 r, int dz) {
         const int iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
         const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
         const float wz = dz ? rz : 1.f - rz;
@@ -404,7 +428,9 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                                    : smem_add_new(cellp + 2, wzy * rx) > 1.f))
             atomicAnd(sbits + (lr * V + ix + 1) / 32, ~(1u << ((ix + 1) & 31)));
         }
-      });
+      };
+      if (PRE2) for_each_touching_point2(touch, tid, C::THREADS, rec0, rec1, scatter_point);
+      else for_each_touching_point(touch, tid, C::THREADS, rec0, scatter_point);
 #endif
       __syncthreads();
       for (int i = tid; i < C::RH * V / 32; i += C::THREADS)
@@ -586,7 +612,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #ifndef DPC_PROBE_NO_GATHER
   if (GATHER) {
     __syncthreads();
-    for_each_touching_point(touch, tid, C::THREADS, rec0, [&](const uint4 r, int dz) {
+    auto gather_point = [&](const uint4 r, int dz) {
       const int n = (int)(r.x >> 16), iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
       const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
       const bool y1 = iy + 1 < V, x1 = ix + 1 < V;   // out-of-range corners carry no gradient
@@ -599,7 +625,9 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       const float sy = wz * (wx0 * (G10 - G00) + rx * (G11 - G01));
       const float sx = wz * (wy0 * (G01 - G00) + ry * (G11 - G10));
       part[((size_t)dz * P + pj) * N + n] = make_float4(dz ? sz : -sz, sy, sx, 0.f);
-    });
+    };
+    if (PRE2) for_each_touching_point2(touch, tid, C::THREADS, rec0, rec1, gather_point);
+    else for_each_touching_point(touch, tid, C::THREADS, rec0, gather_point);
   }
 #endif
 }
