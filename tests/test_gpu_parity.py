@@ -345,3 +345,37 @@ def test_release_and_recreate_internal_streams(dpc):
     b = forward()
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_capped_chunks_match_separate_calls(dpc):
+    """At 64^3 a batch above 128 projections runs as chunks of 64 (64 MiB of grid, api.cu
+    chunk_size) -- 130 projections: 64 + 64 + 2, alternating over the two internal streams.  Every
+    projection must come out as if its chunk had been projected alone."""
+    import ctypes
+    from pytorch_unsup_pc_b200 import _lib, ops
+    dev = torch.device("cuda:0")
+    cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=5)
+    P, N = 130, 200
+    assert _lib.load().dpc_project_chunks(ctypes.byref(ops.make_params(cfg, P, N))) == 3
+    case = _inputs.make_case(cfg, P, N, 777, scale=True, screened=False)
+    kern = CF.smoothing_taps(cfg, 0.8)
+    Wp, Wd = (w.to(dev) for w in _inputs.loss_weights(P, 64))
+
+    def run(sl):
+        leaves = [case[k][sl].to(dev).requires_grad_() for k in ("points", "quat", "scale")]
+        out = dpc.pointcloud_project_fast(cfg, leaves[0], leaves[1], None, None, kern,
+                                          scaling_factor=leaves[2])
+        loss = (out["proj"] * Wp[sl]).sum() + 0.1 * (out["proj_depth"] * Wd[sl]).sum()
+        return out, torch.autograd.grad(loss, leaves)
+
+    dpc.set_outputs(voxels=False, drc_probs=False)
+    try:
+        whole, gw = run(slice(0, P))
+        for sl in (slice(0, 64), slice(64, 128), slice(128, 130)):
+            part, gp = run(sl)
+            for k in ("proj", "proj_depth", "tr_pc"):
+                assert torch.equal(whole[k][sl], part[k]), k      # order-free scatter: bit-equal
+            for a, b in zip(gw, gp):
+                assert torch.equal(a[sl], b)
+    finally:
+        dpc.set_outputs(voxels=True, drc_probs=True)
