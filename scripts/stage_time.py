@@ -14,8 +14,10 @@ import pytorch_unsup_pc_b200 as dpc
 from pytorch_unsup_pc_b200 import _lib, ops
 
 
-def main(workload="A", iters=30, box=0.9):
-    w = bench.WORKLOADS[workload]
+def main(workload="A", iters=30, box=0.9, P=0):
+    w = dict(bench.WORKLOADS[workload])
+    if P:
+        w["P"] = int(P)
     cfg = bench.make_cfg(w)
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -47,9 +49,10 @@ def main(workload="A", iters=30, box=0.9):
     torch.cuda.synchronize()
     t = {k: round(float(v) * 1e3, 1) for k, v in zip(_lib.PROFILE_STAGES, stage_ms)}
     chk = [float(buf[k].double().abs().sum()) for k in ("mask", "depth", "g_points", "g_quat", "g_scale")]
-    print(os.path.basename(_lib.LIB_PATH), workload, "box %.2f" % box, t, "sum %.1f" % sum(t.values()),
+    print(os.path.basename(_lib.LIB_PATH), workload, "P", P, "box %.2f" % box, t, "sum %.1f" % sum(t.values()),
           "chk", " ".join("%.6e" % c for c in chk))
 
 
 if __name__ == "__main__":
-    main(*(sys.argv[1:2] or ["A"]), *[int(x) for x in sys.argv[2:3]], *[float(x) for x in sys.argv[3:4]])
+    main(*(sys.argv[1:2] or ["A"]), *[int(x) for x in sys.argv[2:3]], *[float(x) for x in sys.argv[3:4]],
+         *[int(x) for x in sys.argv[4:5]])
