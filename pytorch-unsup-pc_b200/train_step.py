@@ -134,7 +134,8 @@ class GraphedTrainStep:
     backward.  Follows PyTorch's recipe for DDP under whole-network capture: the DDP wrapper is
     built on a side stream, >= 11 eager iterations run before the capture, Adam is capturable."""
 
-    def __init__(self, nets, cfg, kernel, device, world, example, warmup=11, ddp_kwargs=None):
+    def __init__(self, nets, cfg, kernel, device, world, example, warmup=11, ddp_kwargs=None,
+                 comm_hook=None):
         from torch.nn.parallel import DistributedDataParallel as DDP
         self.cfg, self.kernel, self.device = cfg, kernel, device
         self.images = torch.empty_like(example[0])
@@ -146,6 +147,8 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             self.model = (DDP(nets, device_ids=[device.index], **(ddp_kwargs or {}))
                           if world > 1 else nets)
+            if world > 1 and comm_hook is not None:
+                self.model.register_comm_hook(state=None, hook=comm_hook)
             self.opt = torch.optim.Adam(nets.parameters(), lr=float(cfg.learning_rate),
                                         weight_decay=float(cfg.weight_decay), capturable=True,
                                         fused=True)
@@ -247,6 +250,20 @@ def bench(env, args):
         solo = GraphedTrainStep(fresh_nets(), cfg, kernel, dev, 1, batches[0])
         ms_ns = env.timed(lambda i: solo(*batches[i % 3]), steps, 5)
         del solo
+        # the same captured step with DDP's stock bf16 compression hook: the buckets travel as
+        # bf16 (half the bytes) and are decompressed into the fp32 gradients -- a different
+        # gradient-averaging arithmetic (the reference has no distributed training to compare
+        # with), reported as a variant, never as `value`
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        half = GraphedTrainStep(fresh_nets(), cfg, kernel, dev, world, batches[0], ddp_kwargs=ddp_kw,
+                                comm_hook=default_hooks.bf16_compress_hook)
+        ms_bf = env.timed(lambda i: half(*batches[i % 3]), steps, 5)
+        del half
+        rec["sync_variants"] = {
+            "fp32_buckets (value)": {"ms_per_step": ms / steps, "efficiency_vs_no_collective": ms_ns / ms},
+            "bf16_compress_hook": {"ms_per_step": ms_bf / steps, "efficiency_vs_no_collective": ms_ns / ms_bf,
+                                   "note": "torch.distributed.algorithms.ddp_comm_hooks.default_hooks."
+                                           "bf16_compress_hook: 66.5 MB instead of 133 MB per step"}}
         flat = torch.empty(n_par, dtype=torch.float32, device=dev)
         ms_ar = env.timed(lambda i: dist.all_reduce(flat), steps, 3)
         rec["allreduce"] = {
