@@ -139,3 +139,32 @@ def test_tap_radius_follows_sigma():
     one = torch.ones(1)
     assert lib.dpc_tap_radius(one.data_ptr(), 1) == 0
     assert lib.dpc_tap_radius(one.data_ptr(), 2) == -1
+
+
+def test_render_loss_argument_validation_needs_no_gpu():
+    """The fused step's entry points validate geometry and pointers before any CUDA call: bad
+    arguments come back as DPC_ERR_ARG with a message (no compute on the CPU box)."""
+    import pytorch_unsup_pc_b200 as dpc
+    from pytorch_unsup_pc_b200 import ops
+    lib = dpc._lib.load()
+    cfg = default_cfg(vox_size=64)
+    p = ops.make_params(cfg, 64, 8000)
+    taps = (None, 0, None, 0, None, 0)
+
+    def fwd(replicas, C, G, outputs=0, gt=1):
+        p.outputs = outputs
+        return lib.dpc_render_loss_fwd(ctypes.byref(p), replicas, 8000, None, 1, 1, None, None, None, *taps,
+                                       0, C, G, gt, None, ctypes.c_float(1.0), 1, 1, None, 1, 1, 1, 1, 1,
+                                       1, 1, None, 0, None)
+    assert fwd(4, 3, 128) != 0 and b"replicas" in lib.dpc_last_error()          # 4 is not views x 3
+    assert fwd(4, 4, 100) != 0 and b"GT size" in lib.dpc_last_error()            # 100 is no multiple of 64
+    assert fwd(4, 4, 128, outputs=1) != 0 and b"outputs" in lib.dpc_last_error()
+    assert fwd(5, 5, 128) != 0                                                     # 5 does not divide 64
+    assert fwd(4, 4, 128, gt=None) != 0 and b"NULL" in lib.dpc_last_error()
+    # slots: winner-only where the fast ray state exists (cells, atomic scatter, cubic grid)
+    p.outputs = 0
+    assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 1, 0) == 16
+    assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 0, 0) == 64
+    assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 1, 1) == 64
+    q = ops.make_params(default_cfg(vox_size=64, vox_size_z=32), 64, 8000)
+    assert lib.dpc_render_loss_slots(ctypes.byref(q), 4, 1, 0) == 64
