@@ -1002,9 +1002,12 @@ int dpc_render_loss_bwd(const dpc_params *p, int replicas, int N_src, const int3
   LossGrad lg;
   lg.bmap = winners; lg.gt = gt; lg.pred = mask; lg.kcoef = kcoef; lg.upstream = upstream;
   lg.G = G; lg.C = C;
+  // one view per cloud and no dropout: slot j IS cloud j and the winner's point gradient is the
+  // cloud's -- the pose adjoint writes it in place and the reduction kernel is not launched
+  const bool direct = (replicas / C == 1) && !sel;
   const BwdPtrs q{points, quat, trans, focal, scale, grid_b, clamp_bits, nullptr, nullptr, nullptr,
-                  nullptr, nullptr, g_grid, g_points_rep, g_quat, g_trans, g_focal, g_scale,
-                  const_cast<void *>(cells), rep, const_cast<void *>(cells)};
+                  nullptr, nullptr, g_grid, direct ? g_points : g_points_rep, g_quat, g_trans, g_focal,
+                  g_scale, const_cast<void *>(cells), rep, const_cast<void *>(cells)};
   // the winners as two half-chains on the two internal streams from 64 slots on (as the batch is)
   dpc_params slots = *p;
   slots.P = BV;
@@ -1026,6 +1029,7 @@ int dpc_render_loss_bwd(const dpc_params *p, int replicas, int N_src, const int3
     }
   }
   DPC_TRY(rc);
+  if (direct) return DPC_OK;
   // cloud gradient = sum over the views of a cloud of its winners' point gradients, routed
   // through their dropout selections (autograd of tf_repeat_0 and of the gather)
   return launch_replica_reduce(g_points_rep, sel, inv_scratch, BV, replicas / C, N_src, p->N, 3,
