@@ -63,7 +63,7 @@ namespace dpc {
 #define DPC_BWD_MINB 4         // ... and the backward's (4: 252 registers; 6: 168; 8: 128 + spills)
 #endif
 #ifndef DPC_FWD_L10
-#define DPC_FWD_L10 28         // ring / ray-block length at tap radius 10 (24, 28, 32 measured)
+#define DPC_FWD_L10 32         // ring / ray-block length at tap radius 10 (24, 28, 32 measured; round 2: 32 is 0.6 us ahead in the backward, two ray blocks instead of three)
 #endif
 #ifndef DPC_BWD_THREADS
 #define DPC_BWD_THREADS 64     // ray pairs per backward CTA (32, 64, 128: no difference)
@@ -123,10 +123,14 @@ __device__ __forceinline__ u64 keep_if_equal2(u64 g, u64 x, u64 y) {
 template <int R> struct RingLen { static constexpr int L = 2 * R + 1 + 3; };
 template <> struct RingLen<0> { static constexpr int L = 8; };
 template <> struct RingLen<5> { static constexpr int L = 16; };
-template <int R> struct FwdRingLen { static constexpr int L = RingLen<R>::L; };
-template <> struct FwdRingLen<0> { static constexpr int L = 16; };
-template <> struct FwdRingLen<7> { static constexpr int L = 24; };    // 16 steps of load-ahead, as at radius 10
-template <> struct FwdRingLen<10> { static constexpr int L = DPC_FWD_L10; };
+// (the forward and the fast backward share the length: the forward checkpoints the
+// transmittance at the ray-block starts the backward resumes from.  At radius 10: 32 up to 64^3
+// -- two ray blocks instead of three, backward 35.5 -> 34.8 us -- and 28 at 128^3, where 32 gains
+// 20 us per launch forward but loses 62 backward.)
+template <int R, int V = 64> struct FwdRingLen { static constexpr int L = RingLen<R>::L; };
+template <int V> struct FwdRingLen<0, V> { static constexpr int L = 16; };
+template <int V> struct FwdRingLen<7, V> { static constexpr int L = 24; };    // 16 steps of load-ahead, as at radius 10
+template <int V> struct FwdRingLen<10, V> { static constexpr int L = V <= 64 ? DPC_FWD_L10 : 28; };
 
 struct RayConst {
   int P, Vz;          // P = projections in the whole batch (probs stride)
@@ -206,7 +210,7 @@ __device__ __forceinline__ void pair_index(const RayConst &c, int threads, int &
 template <int V, int R, bool SAVE, int VZ, typename Sink>
 __device__ __forceinline__ void stream_blur_z2(const float *col, float *bs, int Vz_rt,
                                                const Taps<R> &taps, Sink &&sink) {
-  constexpr int W = 2 * R + 1, L = FwdRingLen<R>::L, AHEAD = R + (L - W);   // load-ahead in steps
+  constexpr int W = 2 * R + 1, L = FwdRingLen<R, V>::L, AHEAD = R + (L - W);   // load-ahead in steps
   constexpr int VV = V * V;
   const int Vz = VZ ? VZ : Vz_rt;
   u64 k2[W];
@@ -571,7 +575,7 @@ drc_blurz_bwd_fast_kernel(const float *__restrict__ vgrid, const float *__restri
                           const float *__restrict__ g_depth, float *__restrict__ g_grid,
                           float *__restrict__ scale_partials, int *__restrict__ zero_ints,
                           int n_zero, const LossGrad lg) {
-  constexpr int VZ = V, W = 2 * R + 1, L = FwdRingLen<R>::L, VV = V * V;
+  constexpr int VZ = V, W = 2 * R + 1, L = FwdRingLen<R, V>::L, VV = V * V;
   constexpr int NBLK = (VZ + L - 1) / L, NFULL = VZ / L, NSTORE = VZ > R ? (VZ - R) / L : 0;
   constexpr uint32_t ROW_BYTES = kBwdThreads * sizeof(u64);
   pdl_release();          // head of the backward chain: launched without a programmatic edge
@@ -863,7 +867,7 @@ static void launch_bwd_fast(const DrcArgs &a, const RayConst &c, const Taps<R> &
                             const float *g_mask, const float *g_depth, float *g_grid,
                             float *scale_partials, int *zero_ints, int n_zero, cudaStream_t s,
                             const LossGrad &lg) {
-  constexpr int L = FwdRingLen<R>::L, NBLK = (V + L - 1) / L;
+  constexpr int L = FwdRingLen<R, V>::L, NBLK = (V + L - 1) / L;
   static_assert(NBLK * sizeof(uint64_t) <= 128, "mbarrier area");
   const size_t smem = (size_t)V * kBwdThreads * sizeof(u64) + 128;
   static DeviceOnce attr_once;
