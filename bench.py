@@ -490,7 +490,7 @@ def bench_projection(env, key, full):
     Vz = V
     deterministic = bool(w.get("deterministic"))
     mode = _lib.SCATTER_SORTED if deterministic else _lib.SCATTER_ATOMIC
-    use_cells = not (args.global_grid or deterministic)
+    use_cells = not args.global_grid       # both scatter modes run plane-local and save the same state
     kern = dpc.smoothing_kernel(cfg, w["sigma"])
     taps = ops.host_taps(kern)
     params = ops.make_params(cfg, P, N, flip_y=True)
@@ -749,7 +749,11 @@ def bench_projection(env, key, full):
         "value": value, "unit": UNIT, "ms_per_step": ms_abi / steps, "steps": steps,
         "config": {"workload": w["name"], "P_per_gpu": P, "N": N, "V": V, "Vz": Vz, "K": w["K"],
                    "sigma": w["sigma"],
-                   "scatter": ("deterministic sort-then-segment" if deterministic else
+                   "scatter": ("deterministic sort-then-segment, raw grid in global memory"
+                               if deterministic and args.global_grid else
+                               "deterministic sort-then-segment, plane-local (records sorted by grid "
+                               "row, every plane row summed in a fixed order in shared memory)"
+                               if deterministic else
                                "global grid, atomic" if args.global_grid else "plane-local (shared memory)"),
                    "l2": "no flush: %d input sets rotate and each step's grid + gradient-grid "
                          "working set (%d MiB) exceeds the 126 MB L2" % (
@@ -775,8 +779,9 @@ def bench_projection(env, key, full):
         # kernels per chunk: pose_bin (pose_cells + bin_points above 16384 points; pose_scatter on
         # the global-grid path), blur_xy, blurz_drc_fwd | drc_blurz_bwd, blur_xy, gather_pose_bwd
         # -- times the chunks the batch is split into (whole job: every rank launches its own);
-        # the deterministic mode: records + sort + segment kernels instead of pose_bin (8 per chunk)
-        "gpu_launches": (8 if deterministic else 6 if args.global_grid else
+        # the deterministic mode: records + sort kernels instead of pose_bin (7 per chunk; 8 with
+        # the segment kernel of the global-grid variant)
+        "gpu_launches": ((8 if args.global_grid else 7) if deterministic else 6 if args.global_grid else
                          lib.dpc_project_kernels_per_chunk(ctypes.byref(params)))
                         * n_chunks * steps * world,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,

@@ -136,12 +136,18 @@ DPC_API int dpc_depth_from_probs_bwd(const dpc_params *p, const float *g_depth, 
  * optional outputs and drc_logsum, the clipped ray occupancy v = clip(s B) with
  * the clamp gate in its sign bit), clamp_bits (raw <= 1 mask) and cells
  * (dpc_cells_bytes; NULL ok).
- * With cells != NULL and DPC_SCATTER_ATOMIC the plane-local path runs: the raw
- * grid never exists in global memory -- a pose kernel writes the cell records
- * and every Z-plane is built in shared memory by the blur kernel from the
- * points that touch it (forward), and gathered from shared memory (backward).
- * With cells == NULL (or DPC_SCATTER_SORTED) the grid is scattered in global
- * memory first.  Pass the same cells pointer (or NULL) to dpc_project_bwd.
+ * With cells != NULL the plane-local path runs: the raw grid never exists in
+ * global memory -- a pose kernel writes the cell records and every Z-plane is
+ * built in shared memory by the blur kernel from the points that touch it
+ * (forward), and gathered from shared memory (backward).  DPC_SCATTER_ATOMIC
+ * accumulates a plane with order-free fixed-point shared-memory atomics;
+ * DPC_SCATTER_SORTED sorts the records by grid row first (it needs the
+ * workspace in the forward too) and sums every plane row in a fixed order in
+ * fp32 -- the same sums, bit for bit, as dpc_scatter_fwd's sorted mode.  Both
+ * save the same state, so the backward does not depend on the mode.
+ * With cells == NULL the grid is scattered in global memory first (atomics,
+ * or sort-then-segment).  Pass the same cells pointer (or NULL) to
+ * dpc_project_bwd.
  * voxels/probs are written only when non-NULL.
  * ntaps == 0 means kernel=None (no blur). */
 DPC_API int dpc_project_fwd(const dpc_params *p, const float *points, const float *quat,
@@ -279,7 +285,7 @@ DPC_API int dpc_render_loss_fwd(const dpc_params *p, int replicas, int N_src,
  * NULL when its input is) times the device scalar `upstream` (NULL = 1).
  * The one-hot candidate mask (model_pc_to.py:425-430) makes the gradient of
  * every losing candidate exactly zero: when the forward saved the fast ray
- * state (cells given, atomic scatter, cubic grid, log-sum DRC) the backward
+ * state (cells given, cubic grid, log-sum DRC; either scatter mode) the backward
  * chain runs over the BV winners only and dL/dmask is built inside the ray
  * kernel; otherwise it is written to g_mask_scratch [P,V,V] and the general
  * backward runs.  scatter_mode: the forward's.

@@ -480,10 +480,11 @@ static bool plane_local_ok(const dpc_params *p) {
   return p->N <= 65535 && p->V <= 256 && p->Vz <= 192;
 }
 
-// The DRC kernels' fast saved state (drc.cu): decided from what BOTH passes know.
-static bool fast_ray_state(const dpc_params *p, const void *cells, int scatter_mode) {
+// The DRC kernels' fast saved state (drc.cu): decided from what BOTH passes know -- the cell
+// records and the parameters; the scatter mode does not matter (both modes save the same state).
+static bool fast_ray_state(const dpc_params *p, const void *cells) {
   // (clip value > 0: the saved v >= clip is then strictly positive and its sign bit is free)
-  return cells && scatter_mode == DPC_SCATTER_ATOMIC && p->Vz == p->V && p->outputs == 0 &&
+  return cells && p->Vz == p->V && p->outputs == 0 &&
          p->drc_logsum != 0 && p->drc_clip > 0.0 && p->drc_clip < 0.5;
 }
 static void set_ray_state(DrcArgs &da, const dpc_params *p, void *cells, int b0) {
@@ -526,6 +527,16 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
     b.cells = cells_range(q.cells, p, b0);
     b.Vz = p->Vz; b.N = p->N; b.P = n;
     DPC_TRY(launch_pose_cells(pa, tr_pc, b.cells, s));
+  } else if (q.cells && scatter_mode == DPC_SCATTER_SORTED) {
+    // deterministic plane-local path: pose -> records sorted by grid row + row-segment table;
+    // the blur kernel sums every plane row in a fixed order (no atomics, no raw grid in HBM) and
+    // the saved state is the plane-local one, so the backward does not depend on the mode
+    stage_mark(s);
+    b.cells = cells_range(q.cells, p, b0);
+    b.Vz = p->Vz; b.N = p->N; b.P = n;
+    DPC_TRY(launch_sort_cells(pa, tr_pc, b.cells, sorted_workspace_at(w.sorted, b0, p->N, p->Vz, p->V),
+                              sorted_workspace_bytes(n, p->N, p->Vz, p->V), &b.rowstart,
+                              &b.rowstart_stride, s));
   } else if (scatter_mode == DPC_SCATTER_SORTED) {
     stage_mark(s);
     DPC_TRY(launch_scatter_sorted(&pa, nullptr, n, p->N, p->Vz, p->V, tr_pc, grid,
@@ -543,7 +554,7 @@ static int project_fwd_range(const dpc_params *p, int b0, int n, const FwdPtrs &
   // blur Z + scale + clip + DRC; the blurred occupancy overwrites grid in place (saved for bwd)
   DrcArgs da = drc_args(&sp, grid, q.scale ? q.scale + b0 : nullptr);
   da.P_total = p->P;
-  if (fast_ray_state(p, q.cells, scatter_mode)) set_ray_state(da, p, q.cells, b0);
+  if (fast_ray_state(p, q.cells)) set_ray_state(da, p, q.cells, b0);
   DPC_TRY(launch_blurz_drc_fwd(da, tz, kz, grid, q.mask + b0 * I, q.depth ? q.depth + b0 * I : nullptr,
                                q.voxels ? q.voxels + b0 * G : nullptr,
                                q.probs ? q.probs + b0 * I : nullptr, s));
@@ -566,7 +577,6 @@ static int project_fwd_impl(const dpc_params *p, const Replica &rep, const float
     set_error("project_fwd: params.outputs=%d does not match the voxels / probs pointers", p->outputs);
     return DPC_ERR_ARG;
   }
-  if (scatter_mode == DPC_SCATTER_SORTED) cells = nullptr;   // the sorted scatter builds the grid itself
   if (!plane_local_ok(p)) cells = nullptr;
   DPC_TRY(check_taps(tx, kx, "taps_x")); DPC_TRY(check_taps(ty, ky, "taps_y"));
   DPC_TRY(check_taps(tz, kz, "taps_z"));
@@ -716,7 +726,7 @@ static int project_bwd_impl(const dpc_params *p, const Replica &rep, const float
   const Workspace w = carve(p, workspace);
   cudaStream_t s = (cudaStream_t)stream;
   void *fast_rays = nullptr;
-  if (plane_local_ok(p) && fast_ray_state(p, cells, DPC_SCATTER_ATOMIC)) {
+  if (plane_local_ok(p) && fast_ray_state(p, cells)) {
     if (g_probs || g_voxels) {
       set_error("project_bwd: g_probs / g_voxels given but params.outputs says the forward did "
                 "not materialise them");
@@ -866,8 +876,8 @@ int dpc_candidate_loss_bwd(int BV, int C, int V, int G, const float *gt, const f
 // saved the fast ray state the backward chain therefore runs over the BV winners (chain slots,
 // bmap = winners) and the ray kernel builds dL/dmask on the fly; otherwise dL/dmask is written
 // out for all P projections and the general backward runs.
-static bool render_winner_only(const dpc_params *p, const void *cells, int scatter_mode) {
-  return plane_local_ok(p) && fast_ray_state(p, cells, scatter_mode);
+static bool render_winner_only(const dpc_params *p, const void *cells) {
+  return plane_local_ok(p) && fast_ray_state(p, cells);
 }
 
 static int check_render_args(const dpc_params *p, int replicas, int C, int G) {
@@ -884,7 +894,8 @@ static int check_render_args(const dpc_params *p, int replicas, int C, int G) {
 
 int dpc_render_loss_slots(const dpc_params *p, int num_candidates, int have_cells, int scatter_mode) {
   if (!p || p->P < 1 || num_candidates < 1 || p->P % num_candidates) return 0;
-  return render_winner_only(p, have_cells ? (const void *)p : nullptr, scatter_mode)
+  (void)scatter_mode;     // both scatter modes save the same state
+  return render_winner_only(p, have_cells ? (const void *)p : nullptr)
              ? p->P / num_candidates : p->P;
 }
 
@@ -978,8 +989,8 @@ int dpc_render_loss_bwd(const dpc_params *p, int replicas, int N_src, const int3
   if (sel) DPC_REQUIRE(inv_scratch);
   const int C = num_candidates, BV = p->P / C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (scatter_mode == DPC_SCATTER_SORTED) cells = nullptr;
-  if (!render_winner_only(p, cells, scatter_mode)) {
+  (void)scatter_mode;     // the saved state does not depend on it (see fast_ray_state)
+  if (!render_winner_only(p, cells)) {
     // general saved state: dL/dmask for all P projections (zeros for the losers), then the
     // replica-aware backward
     DPC_REQUIRE(g_mask_scratch);
@@ -1075,7 +1086,7 @@ int dpc_project_profile(const dpc_params *p, const float *points, const float *q
     const int nf = tl_stage_idx;  // 5 events: start + 4 stages
     if (rc == DPC_OK)
       rc = dpc_project_bwd(p, points, quat, trans, focal, scale, tx, kx, ty, ky, tz, kz, grid_b,
-                           clamp_bits, scatter_mode == DPC_SCATTER_SORTED ? nullptr : cells, g_mask,
+                           clamp_bits, cells, g_mask,
                            g_depth, nullptr, nullptr, nullptr, g_grid, g_points, g_quat, g_trans,
                            g_focal, g_scale, workspace, workspace_bytes, stream);
     const int nb = tl_stage_idx;  // + 5 events

@@ -302,14 +302,20 @@ __device__ __forceinline__ uint32_t le1_nibble(float4 v) {
 // SLOTS: the winner-only backward of render_loss (plane slots addressed through bmap).  A
 // template parameter, not a run-time branch: at 56 registers (9 CTAs per SM) the slot / plane
 // index pair costs the plain kernel 2.7 us per launch (47.1 vs 44.4 us at workload A).
-template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT, bool POINTS, bool SLOTS = false>
+// DET: the deterministic plane build of the sort-then-segment mode (forward, POINTS): the records
+// are sorted by grid row and one thread per plane row sums its four row segments in a fixed order
+// (see scatter_sorted.cu) -- plain fp32 adds into the thread's own row, no atomics.
+template <int V, int R, bool CLAMP_IN, bool WRITE_BITS, bool MASK_OUT, bool POINTS, bool SLOTS = false,
+          bool DET = false>
 __global__ void __launch_bounds__(XYCfg<V, R>::THREADS, XYCfg<V, R>::MINB)
 blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
                uint32_t *__restrict__ bits_out, const uint32_t *__restrict__ bits_in,
                const Taps<R> kx, const Taps<R> ky, const CellsView cells,
-               float4 *__restrict__ part, int Vz, int N, int P, const int *__restrict__ bmap) {
+               float4 *__restrict__ part, int Vz, int N, int P, const int *__restrict__ bmap,
+               const uint32_t *__restrict__ rowstart, size_t rowstart_stride) {
   using C = XYCfg<V, R>;
   static_assert(!POINTS || (WRITE_BITS != MASK_OUT), "POINTS: forward (bits out) or backward (mask)");
+  static_assert(!DET || (POINTS && WRITE_BITS && C::THREADS >= C::RH), "DET: plane-local forward, a thread per row");
   constexpr int HALF = C::RH / 2;
   extern __shared__ __align__(16) float2 smem2[];
   float2 *A2 = smem2;                  // [RH/2][S]  (row r, row r + RH/2), x padded by R
@@ -345,12 +351,26 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #define DPC_XY_PREFETCH2_BWD 0   // measured: no difference in the backward gather (39.7 vs 39.8 us)
 #endif
   // (not with SLOTS: the slot / plane index pair leaves no room for four more registers)
-  constexpr bool PRE2 = POINTS && (WRITE_BITS || (DPC_XY_PREFETCH2_BWD && !SLOTS)) && DPC_XY_PREFETCH &&
-                        DPC_XY_PREFETCH2;
+  constexpr bool PRE2 = POINTS && !DET && (WRITE_BITS || (DPC_XY_PREFETCH2_BWD && !SLOTS)) &&
+                        DPC_XY_PREFETCH && DPC_XY_PREFETCH2;
   if (POINTS && DPC_XY_PREFETCH) {
     touch = touch_range(cells, pb, pz, N);
-    rec0 = first_touching_record(touch, tid);
+    if (!DET) rec0 = first_touching_record(touch, tid);
     if (PRE2) rec1 = second_touching_record(touch, tid, C::THREADS);
+  }
+  // DET: the bounds of this thread's four row segments -- rows (pz - dz, y - 1) and (pz - dz, y)
+  // are neighbours in the table, so three entries per dz -- requested now, used after the zeroing
+  uint32_t seg[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
+  if (DET && C::RH == V && tid < V) {
+    const uint32_t *rs = rowstart + (size_t)pb * rowstart_stride;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz) {
+      const int k = (pz - dz) * V + tid;              // row (pz - dz, y = tid)
+      if (pz - dz < 0) continue;
+      seg[dz][1] = ld_dep(rs + k);
+      seg[dz][2] = ld_dep(rs + k + 1);
+      seg[dz][0] = tid > 0 ? ld_dep(rs + k - 1) : seg[dz][1];
+    }
   }
   // A plane no point touches (real clouds fill a fraction of the frustum's depth): forward, its
   // raw occupancy is zero, so both blur passes give zero and every raw <= 1 bit is set; backward,
@@ -382,7 +402,7 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
   // tile is 11 vector stores per thread)
   // fixed-point plane scatter (one-tile layouts): the tile starts as the bias 1.0f, pads included,
   // so that the X pass decodes every window element alike; the pads are zeroed for the Y pass
-  constexpr bool FIXED = POINTS && WRITE_BITS && C::ONE_TILE && DPC_XY_FIXED;
+  constexpr bool FIXED = POINTS && WRITE_BITS && C::ONE_TILE && DPC_XY_FIXED && !DET;
   if ((POINTS && WRITE_BITS) || !DPC_XY_PADZERO || V < 128) {
     // the scatter accumulates into the tile: all of it starts at zero (at the bias when FIXED)
     const float z0 = FIXED ? 1.f : 0.f;
@@ -421,7 +441,62 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
 #ifndef DPC_PROBE_NO_SCATTER
       if (!DPC_XY_PREFETCH) {
         touch = touch_range(cells, pb, pz, N);
-        rec0 = first_touching_record(touch, tid);
+        if (!DET) rec0 = first_touching_record(touch, tid);
+      }
+      if (DET) {
+        // ---- deterministic build: thread lr sums plane row y = h*RH + lr ----
+        // Row (z, y) receives the points of the four base rows (z - dz, y - dy); the walk order
+        // -- dz = 0 then 1, inside it dy = 0 then 1, inside a segment ascending sorted position
+        // (= ascending point index) -- and the weight products are segment_rows_kernel's
+        // (scatter_sorted.cu), so the plane is bit-identical to the stand-alone sorted scatter.
+        if (tid < C::RH) {
+          const int lr = tid, y = h * C::RH + lr;
+          if (C::RH != V) {         // several rounds per plane: the bounds of this round's row
+            const uint32_t *rs = rowstart + (size_t)pb * rowstart_stride;
+#pragma unroll
+            for (int dz = 0; dz < 2; ++dz) {
+              const int k = (pz - dz) * V + y;
+              if (pz - dz < 0) continue;
+              seg[dz][1] = ld_dep(rs + k);
+              seg[dz][2] = ld_dep(rs + k + 1);
+              seg[dz][0] = y > 0 ? ld_dep(rs + k - 1) : seg[dz][1];
+            }
+          }
+          float *rowp = reinterpret_cast<float *>(A2 + (lr % HALF) * C::S + R) + lr / HALF;
+          uint32_t *rbits = sbits + lr * (V / 32);
+          const uint4 *sr = cells.srec + (size_t)pb * N;
+          // first record of every segment in flight before the first add
+          uint4 head[2][2];
+#pragma unroll
+          for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const uint32_t i0 = seg[dz][1 - dy], i1 = seg[dz][2 - dy];
+              head[dz][dy] = i0 < i1 ? ld_dep(sr + i0) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+          for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const uint32_t i0 = seg[dz][1 - dy], i1 = seg[dz][2 - dy];
+              uint4 nxt = head[dz][dy];
+              for (uint32_t i = i0; i < i1; ++i) {
+                const uint4 r = nxt;
+                if (i + 1 < i1) nxt = ld_dep(sr + i + 1);
+                const int ix = (int)(r.x & 0xFFu);
+                const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
+                const float wzy = (dz ? rz : 1.f - rz) * (dy ? ry : 1.f - ry);
+                float nv = fmaf(wzy, 1.f - rx, rowp[2 * ix]);
+                rowp[2 * ix] = nv;
+                if (nv > 1.f) rbits[ix >> 5] &= ~(1u << (ix & 31));
+                if (ix + 1 < V) {
+                  nv = fmaf(wzy, rx, rowp[2 * ix + 2]);
+                  rowp[2 * ix + 2] = nv;
+                  if (nv > 1.f) rbits[(ix + 1) >> 5] &= ~(1u << ((ix + 1) & 31));
+                }
+              }
+            }
+        }
       }
       auto scatter_point = [&](const uint4 r, int dz) {
         const int iy = (int)((r.x >> 8) & 0xFFu), ix = (int)(r.x & 0xFFu);
@@ -441,7 +516,8 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
             atomicAnd(sbits + (lr * V + ix + 1) / 32, ~(1u << ((ix + 1) & 31)));
         }
       };
-      if (PRE2) for_each_touching_point2(touch, tid, C::THREADS, rec0, rec1, scatter_point);
+      if (DET) { /* built above */ }
+      else if (PRE2) for_each_touching_point2(touch, tid, C::THREADS, rec0, rec1, scatter_point);
       else for_each_touching_point(touch, tid, C::THREADS, rec0, scatter_point);
 #endif
       __syncthreads();
@@ -661,12 +737,17 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     }                                                                                          \
     launch_dep(blur_xy_kernel<V, R, CL, WB, MO, PT, ##__VA_ARGS__>, g, t, smem, s, a.src,      \
-               a.dst, a.bits_out, a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P, a.bmap); \
+               a.dst, a.bits_out, a.bits_in, KX, KY, a.cells, a.part, a.Vz, a.N, a.P, a.bmap, \
+               a.rowstart, a.rowstart_stride);                                                 \
   } while (0)
   const bool points = a.cells.cellz != nullptr;
   if (points && (a.Vz < 1 || a.N < 1 || a.P < 1 || (!a.bits_in && !a.bits_out) ||
                  (a.bits_in && !a.part))) {
     set_error("blur_xy: plane-local scatter/gather needs Vz, N, P and bits (and part backward)");
+    return DPC_ERR_ARG;
+  }
+  if (a.rowstart && !(points && a.bits_out)) {
+    set_error("blur_xy: the row-segment table (rowstart) exists on the plane-local forward only");
     return DPC_ERR_ARG;
   }
   if (a.bmap && !(points && a.bits_in)) {
@@ -679,7 +760,8 @@ static int launch_vr(const BlurXYArgs &a, const float *tx, int kx, const float *
     else DPC_LAUNCH_XY(false, false, true, false);
   } else if (a.bits_out) {
     if (!a.clamp_in) { set_error("blur_xy: bits_out requires clamp_in"); return DPC_ERR_ARG; }
-    if (points) DPC_LAUNCH_XY(true, true, false, true);
+    if (points && a.rowstart) DPC_LAUNCH_XY(true, true, false, true, false, true);
+    else if (points) DPC_LAUNCH_XY(true, true, false, true);
     else DPC_LAUNCH_XY(true, true, false, false);
   } else if (a.clamp_in) {
     DPC_LAUNCH_XY(true, false, false, false);

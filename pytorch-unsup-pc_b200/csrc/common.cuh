@@ -235,6 +235,11 @@ int launch_scatter_trpc(const float *tr_pc, int P, int N, int Vz, int V, float *
 int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N, int Vz, int V,
                           float *tr_pc_out, float *grid, void *ws, size_t ws_bytes,
                           cudaStream_t s);
+// ... as the plane-local path's saved state (see scatter_sorted.cu): the sorted records, z-cell
+// bytes and boundaries go to `cells`, the row-segment table stays in the workspace
+int launch_sort_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, void *ws,
+                      size_t ws_bytes, const uint32_t **rowstart, size_t *rowstart_stride,
+                      cudaStream_t s);
 size_t sorted_workspace_bytes(int P, int N, int Vz, int V);
 void *sorted_workspace_at(void *ws, int b0, int N, int Vz, int V);   // projections [b0, ...) of a batch
 
@@ -305,6 +310,12 @@ struct BlurXYArgs {
   // winner-only backward: plane slot j*Vz + z holds the gradient plane of projection bmap[j]
   // (bits_in and cells are indexed by the real projection, src / part by the slot)
   const int *bmap = nullptr;
+  // deterministic plane build (forward, plane-local): cells.srec is sorted by grid row
+  // (iz * V + iy, ascending point index inside a row) and rowstart[b * rowstart_stride + r] is
+  // the first record of row r of projection b (launch_sort_cells); every plane row is then summed
+  // by ONE thread in a fixed order instead of by shared-memory atomics
+  const uint32_t *rowstart = nullptr;
+  size_t rowstart_stride = 0;
 };
 int launch_blur_xy(const BlurXYArgs &a, const float *tx, int kx, const float *ty, int ky,
                    cudaStream_t s);

@@ -23,6 +23,14 @@
 //     and its summation order is a pure function of the inputs.
 // Round 2: records + shared-memory sort + segment table (workload C5's scatter
 // stage: 241 us -> see DESIGN.md section 5).
+//
+// Plane-local variant (launch_sort_cells; the whole-projection path when the caller passes a
+// cell-record buffer): the first two kernels are the same, but they write the plane-local path's
+// saved state -- z-cell bytes, records {n << 16 | iy << 8 | ix, fractions} sorted by row (hence by
+// z cell), the z-cell boundaries -- and step 2 happens INSIDE the blur-XY kernel (blur_xy.cu,
+// DET): the CTA that owns plane z builds it in shared memory, one thread per row walking the
+// same four segments in the same order.  The raw grid never reaches HBM, the sums are the very
+// sums of segment_rows_kernel (bit-identical planes), and the backward is the plane-local one.
 #include "common.cuh"
 #include "pose.cuh"
 
@@ -94,25 +102,37 @@ __device__ __forceinline__ Cell point_cell(const PointSource &src, int b, int n,
 // One thread per point: the cell of every point is derived ONCE (fp64 pose, as everywhere) and
 // kept as a record {ix, rz, ry, rx} (fp32 fractions, as on the default path) next to its sort item
 // key << 16 | n (key = base grid row iz * V + iy; Vz * V for out-of-frustum points).
+template <bool CELLS>
 __global__ void __launch_bounds__(kItemThreads)
 sort_items_kernel(PointSource src, float *__restrict__ tr_out, void *ws, size_t stride, int N,
-                  int Vz, int V) {
+                  int Vz, int V, CellsView cells) {
   const int b = blockIdx.y, n = blockIdx.x * kItemThreads + threadIdx.x;
+  if (CELLS && n >= N && n < cells.Npad) cells.cellz[(size_t)b * cells.Npad + n] = (uint8_t)kCellNone;
   if (n >= N) return;
   const SortedView sv = sorted_view(ws, stride, b, N);
   const Cell c = point_cell(src, b, n, N, Vz, V, tr_out);
   const uint32_t key = c.valid ? (uint32_t)(c.iz * V + c.iy) : (uint32_t)(Vz * V);
   sv.A[n] = (key << 16) | (uint32_t)n;
-  sv.rec[n] = make_uint4((uint32_t)c.ix, __float_as_uint((float)c.rz), __float_as_uint((float)c.ry),
-                         __float_as_uint((float)c.rx));
+  if (CELLS) {
+    // the plane-local path's record (common.cuh CellsView): the point index and the in-plane
+    // cell ride in the first word; the z-cell byte tells the backward which partials exist
+    cells.cellz[(size_t)b * cells.Npad + n] = (uint8_t)(c.valid ? (unsigned)c.iz : kCellNone);
+    cells.rec[(size_t)b * N + n] =
+        make_uint4(((uint32_t)n << 16) | (((uint32_t)c.iy & 0xFFu) << 8) | ((uint32_t)c.ix & 0xFFu),
+                   __float_as_uint((float)c.rz), __float_as_uint((float)c.ry),
+                   __float_as_uint((float)c.rx));
+  } else {
+    sv.rec[n] = make_uint4((uint32_t)c.ix, __float_as_uint((float)c.rz), __float_as_uint((float)c.ry),
+                           __float_as_uint((float)c.rx));
+  }
 }
 
 // One CTA per projection: the items are sorted in SHARED memory when the cloud fits (SMEM; else in
 // the two global buffers), and the start of every grid row's segment is tabulated, so that the
 // last kernel neither recomputes a pose nor searches.
-template <bool SMEM>
+template <bool SMEM, bool CELLS>
 __global__ void __launch_bounds__(kSortThreads)
-sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V) {
+sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cells) {
   extern __shared__ uint32_t sm_sort[];           // cnt [16 * threads] | SMEM: A [N] | B [N]
   __shared__ uint32_t warp_tot[kSortThreads / 32];
   uint32_t *cnt = sm_sort, *sm_items = sm_sort + 16 * kSortThreads;
@@ -168,13 +188,23 @@ sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V) {
   // 4 passes: the sorted array ends in A.  Segment starts: rowstart[k] = first index whose key
   // is >= k, for k = 0 .. rows + 1 (rowstart[rows] = the first out-of-frustum point,
   // rowstart[rows + 1] = N); the sorted items go to the global buffer the second kernel reads
+  const uint4 *rec = CELLS ? cells.rec + (size_t)b * N : sv.rec;
+  uint4 *srec = CELLS ? cells.srec + (size_t)b * N : sv.srec;
+  uint32_t *bs = CELLS ? cells.binstart + (size_t)b * cells.zstride : nullptr;
   for (int i = tid; i < N; i += kSortThreads) {
     const uint32_t item = A[i], key = item >> 16;
-    sv.srec[i] = sv.rec[item & 0xffffu];          // the records in sorted order: sequential reads later
+    srec[i] = rec[item & 0xffffu];                // the records in sorted order: sequential reads later
     const uint32_t prev = i > 0 ? (A[i - 1] >> 16) + 1u : 0u;
-    for (uint32_t k = prev; k <= key; ++k) sv.rowstart[k] = (uint32_t)i;
+    for (uint32_t k = prev; k <= key; ++k) {
+      sv.rowstart[k] = (uint32_t)i;
+      // rows are z-major: the first row of a z cell starts the cell (k == rows: the valid total)
+      if (CELLS && k % (uint32_t)V == 0) bs[k / (uint32_t)V] = (uint32_t)i;
+    }
     if (i == N - 1)
-      for (uint32_t k = key + 1; k <= rows + 1; ++k) sv.rowstart[k] = (uint32_t)N;
+      for (uint32_t k = key + 1; k <= rows + 1; ++k) {
+        sv.rowstart[k] = (uint32_t)N;
+        if (CELLS && k <= rows && k % (uint32_t)V == 0) bs[k / (uint32_t)V] = (uint32_t)N;
+      }
   }
 }
 
@@ -203,8 +233,9 @@ segment_rows_kernel(const void *ws, size_t stride, int N, int Vz, int V, float *
           const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
           // the same fp32 weight products as the default plane scatter (blur_xy.cu)
           const float wzy = (dz ? rz : 1.f - rz) * (dy ? ry : 1.f - ry);
-          acc[ix * S + tid] += wzy * (1.f - rx);
-          if (ix + 1 < V) acc[(ix + 1) * S + tid] += wzy * rx;
+          // (explicit fused multiply-adds: the plane-local build in blur_xy.cu spells the same)
+          acc[ix * S + tid] = fmaf(wzy, 1.f - rx, acc[ix * S + tid]);
+          if (ix + 1 < V) acc[(ix + 1) * S + tid] = fmaf(wzy, rx, acc[(ix + 1) * S + tid]);
         }
       }
   }
@@ -218,9 +249,11 @@ segment_rows_kernel(const void *ws, size_t stride, int N, int Vz, int V, float *
   }
 }
 
-int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N, int Vz, int V,
-                          float *tr_pc_out, float *grid, void *ws, size_t ws_bytes,
-                          cudaStream_t s) {
+// the first two kernels: items + records, then the per-projection sort and the row-segment table
+// (cells != NULL: records, z-cell bytes and z-cell boundaries in the plane-local layout)
+static int launch_sort(const PoseArgs *a, const float *tr_pc_in, int P, int N, int Vz, int V,
+                       float *tr_pc_out, const CellsView *cells, void *ws, size_t ws_bytes,
+                       cudaStream_t s) {
   if (N > 65536 || Vz * V >= 65535) {
     set_error("sorted scatter: needs N <= 65536 and Vz*V < 65535");
     return DPC_ERR_ARG;
@@ -239,23 +272,41 @@ int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N
     src.tr_pc = tr_pc_in;
   }
   const size_t stride = sorted_stride_bytes(N, Vz, V);
-  sort_items_kernel<<<dim3((N + kItemThreads - 1) / kItemThreads, P), kItemThreads, 0, s>>>(
-      src, a ? tr_pc_out : nullptr, ws, stride, N, Vz, V);
+  const CellsView cv = cells ? *cells : CellsView{nullptr, nullptr, nullptr, nullptr, 0, 0};
+  const int n_items = cells ? cv.Npad : N;       // the padding z-cell bytes are written too
+  const dim3 gi((n_items + kItemThreads - 1) / kItemThreads, P);
+  if (cells)
+    sort_items_kernel<true><<<gi, kItemThreads, 0, s>>>(src, a ? tr_pc_out : nullptr, ws, stride, N,
+                                                        Vz, V, cv);
+  else
+    sort_items_kernel<false><<<gi, kItemThreads, 0, s>>>(src, a ? tr_pc_out : nullptr, ws, stride,
+                                                         N, Vz, V, cv);
   if (int e = check_launch("sort_items")) return e;
   const size_t cnt_smem = (size_t)16 * kSortThreads * sizeof(uint32_t);
   static DeviceOnce sort_once;
   if (sort_once.first()) {
-    cudaFuncSetAttribute(sort_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)cnt_smem + 2 * kSmemSortMax * (int)sizeof(uint32_t));
-    cudaFuncSetAttribute(sort_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const int big = (int)cnt_smem + 2 * kSmemSortMax * (int)sizeof(uint32_t);
+    cudaFuncSetAttribute(sort_points_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(sort_points_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(sort_points_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)cnt_smem);
+    cudaFuncSetAttribute(sort_points_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)cnt_smem);
   }
-  if (N <= kSmemSortMax)
-    sort_points_kernel<true><<<P, kSortThreads, cnt_smem + (size_t)2 * N * sizeof(uint32_t), s>>>(
-        ws, stride, N, Vz, V);
-  else
-    sort_points_kernel<false><<<P, kSortThreads, cnt_smem, s>>>(ws, stride, N, Vz, V);
-  if (int e = check_launch("sort_points")) return e;
+  const bool in_smem = N <= kSmemSortMax;
+  const size_t smem = cnt_smem + (in_smem ? (size_t)2 * N * sizeof(uint32_t) : 0);
+  if (in_smem && cells) sort_points_kernel<true, true><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
+  else if (in_smem) sort_points_kernel<true, false><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
+  else if (cells) sort_points_kernel<false, true><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
+  else sort_points_kernel<false, false><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
+  return check_launch("sort_points");
+}
+
+int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N, int Vz, int V,
+                          float *tr_pc_out, float *grid, void *ws, size_t ws_bytes,
+                          cudaStream_t s) {
+  if (int e = launch_sort(a, tr_pc_in, P, N, Vz, V, tr_pc_out, nullptr, ws, ws_bytes, s)) return e;
+  const size_t stride = sorted_stride_bytes(N, Vz, V);
   const size_t smem = (size_t)V * (kRowThreads + 1) * sizeof(float);
   static DeviceOnce attr_once;
   if (attr_once.first()) {
@@ -265,6 +316,19 @@ int launch_scatter_sorted(const PoseArgs *a, const float *tr_pc_in, int P, int N
   dim3 g((Vz * V + kRowThreads - 1) / kRowThreads, P);
   segment_rows_kernel<<<g, kRowThreads, smem, s>>>(ws, stride, N, Vz, V, grid);
   return check_launch("segment_rows");
+}
+
+// Plane-local variant: pose -> tr_pc (NULL ok) + the sorted cell records; the planes themselves
+// are built by the blur-XY kernel from `rowstart` (row r of projection b: rowstart[b * stride + r],
+// stride in 32-bit words)
+int launch_sort_cells(const PoseArgs &a, float *tr_pc, const CellsView &cells, void *ws,
+                      size_t ws_bytes, const uint32_t **rowstart, size_t *rowstart_stride,
+                      cudaStream_t s) {
+  if (int e = launch_sort(&a, nullptr, a.P, a.N, a.Vz, a.V, tr_pc, &cells, ws, ws_bytes, s)) return e;
+  const size_t stride = sorted_stride_bytes(a.N, a.Vz, a.V);
+  *rowstart = sorted_view(ws, stride, 0, a.N).rowstart;
+  *rowstart_stride = stride / sizeof(uint32_t);
+  return DPC_OK;
 }
 
 // the workspace of projections [b0, ...) inside a whole-batch workspace

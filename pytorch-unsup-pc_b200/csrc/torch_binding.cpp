@@ -71,7 +71,7 @@ class ProjectFunction : public torch::autograd::Function<ProjectFunction> {
     Tensor voxels = want_voxels ? torch::empty({p.P, p.Vz, p.V, p.V}, f32) : Tensor();
     Tensor probs = want_probs ? torch::empty({p.Vz + 1, p.P, p.V, p.V}, f32) : Tensor();
     // saved state, one allocation: blurred grid | clamp bits | cell records + ray checkpoints
-    const bool use_cells = mode == DPC_SCATTER_ATOMIC && plane_local;
+    const bool use_cells = plane_local;   // both scatter modes save the plane-local state
     const int64_t n_grid = (int64_t)p.P * p.Vz * p.V * p.V * 4;
     const int64_t n_bits = (int64_t)p.P * p.Vz * p.V * (p.V / 32) * 4;
     const int64_t n_cells = use_cells ? (int64_t)dpc_cells_bytes(&p) : 0;

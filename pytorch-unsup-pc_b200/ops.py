@@ -147,8 +147,9 @@ class ProjectFn(torch.autograd.Function):
     forward : pose + cell records, plane scatter + blur XY, blur Z/DRC   (3 launches)
     backward: DRC reverse scan/blur Z adjoint, blur XY adjoint + plane gather,
               pose adjoint with fused final reductions                   (3 launches)
-    (``plane_local=False`` or the deterministic mode: memset + global scatter
-    forward, grid gather backward.)
+    (the deterministic mode: items + sort in front of the plane kernel, which then sums
+    every plane row in a fixed order; ``plane_local=False``: memset + global scatter -- or
+    the stand-alone sorted scatter -- forward, grid gather backward.)
     Saved for backward: the inputs, the blurred grid, a 1-bit clamp mask and
     the per-point cell records.
     """
@@ -170,7 +171,7 @@ class ProjectFn(torch.autograd.Function):
         probs = torch.empty(Vz + 1, P, V, V, **f32) if want_probs else None
         # state saved for the backward, ONE allocation: blurred grid | clamp bits | per-point
         # cell records (plane-local scatter/gather path, the default mode)
-        use_cells = int(mode) == _lib.SCATTER_ATOMIC and plane_local
+        use_cells = bool(plane_local)      # both scatter modes save the plane-local state
         n_grid = P * Vz * V * V * 4
         n_bits = P * Vz * V * (V // 32) * 4
         n_cells = _sizes(params)[1] if use_cells else 0
@@ -289,7 +290,7 @@ class RenderLossFn(torch.autograd.Function):
         small = torch.empty(3 * BV + 1, **f32)
         view_loss, kcoef, loss = small[:BV], small[BV:2 * BV], small[2 * BV:2 * BV + 1]
         winners = small[2 * BV + 1:].view(torch.int32)
-        use_cells = int(mode) == _lib.SCATTER_ATOMIC and plane_local
+        use_cells = bool(plane_local)      # both scatter modes save the plane-local state
         n_grid = P * Vz * V * V * 4
         n_bits = P * Vz * V * (V // 32) * 4
         n_cells = _sizes(params)[1] if use_cells else 0

@@ -310,6 +310,32 @@ def test_plane_local_path_matches_global_grid_path(dpc, V, N, sigma, kind):
         assert _golden.rel_err(grads_p[k], grads_g[k]) < GRAD_TOL, k
 
 
+@pytest.mark.parametrize("V,N,sigma,kind", [(64, 8000, 3.0, "uniform"), (32, 1500, 0.7, "clustered"),
+                                            (128, 4000, 3.0, "uniform"), (64, 300, 1.0, "clustered")])
+def test_sorted_plane_build_equals_standalone_sorted_scatter(dpc, V, N, sigma, kind):
+    """Deterministic mode: the plane kernel sums every plane row from the row-sorted records in
+    the order of the stand-alone sort-then-segment scatter (which writes the raw grid to global
+    memory), so every forward output is BIT-identical between the two; the backward (plane
+    gather vs grid gather) agrees to rounding.  Includes a pile of points in one cell (raw > 1:
+    the clamp and its gate bits) and a translated, focal-scaled pose (points leave the frustum)."""
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=21 if V > 32 else 11)
+    case = _inputs.make_case(cfg, 3, N, 177 + V, kind=kind, translation=True, focal=True,
+                             screened=False)
+    case["points"][2, : N // 2] = case["points"][2, 0]          # N/2 points in ONE cell
+    case["kernel"] = CF.smoothing_taps(cfg, sigma)
+    with dpc.options(deterministic=True):
+        out_p, loss_p, grads_p = run_cuda(dpc, cfg, case, 3, V)
+        out_p2, _, grads_p2 = run_cuda(dpc, cfg, case, 3, V)
+        with dpc.options(plane_local=False):
+            out_g, loss_g, grads_g = run_cuda(dpc, cfg, case, 3, V)
+    for k in ("proj", "proj_depth", "tr_pc", "voxels", "drc_probs"):
+        assert torch.equal(out_p[k], out_g[k]), k
+        assert torch.equal(out_p[k], out_p2[k]), k
+    for k in grads_p:
+        assert torch.equal(grads_p[k], grads_p2[k]), k
+        assert _golden.rel_err(grads_p[k], grads_g[k]) < GRAD_TOL, k
+
+
 def test_release_and_recreate_internal_streams(dpc):
     """dpc_release() destroys the calling thread's internal side streams / events (the only state
     the library keeps); the next batch of >= 64 projections re-creates them and gives the same bits."""

@@ -161,10 +161,11 @@ def test_render_loss_argument_validation_needs_no_gpu():
     assert fwd(4, 4, 128, outputs=1) != 0 and b"outputs" in lib.dpc_last_error()
     assert fwd(5, 5, 128) != 0                                                     # 5 does not divide 64
     assert fwd(4, 4, 128, gt=None) != 0 and b"NULL" in lib.dpc_last_error()
-    # slots: winner-only where the fast ray state exists (cells, atomic scatter, cubic grid)
+    # slots: winner-only where the fast ray state exists (cells, either scatter mode, cubic grid)
     p.outputs = 0
     assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 1, 0) == 16
     assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 0, 0) == 64
-    assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 1, 1) == 64
+    assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 1, 1) == 16
+    assert lib.dpc_render_loss_slots(ctypes.byref(p), 4, 0, 1) == 64
     q = ops.make_params(default_cfg(vox_size=64, vox_size_z=32), 64, 8000)
     assert lib.dpc_render_loss_slots(ctypes.byref(q), 4, 1, 0) == 64

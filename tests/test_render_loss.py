@@ -6,7 +6,7 @@ CPU: the oracle composition against vectors made by the REAL reference's own com
 (loss / projections 1e-5, gradients 1e-4, argmin equal), against the composition of the three
 separate CUDA ops (bit-identical: same kernels, same winner arithmetic, the skipped candidates'
 gradients are exact zeros), with the two half-chains of the winner-only backward (>= 64 views)
-and through the general saved-state path (deterministic scatter).
+in the deterministic mode, and through the general saved-state path (raw grid in global memory).
 """
 import os
 
@@ -97,14 +97,17 @@ def _composed(dpc, cfg, spec, t, kernel, idx):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("deterministic", [False, True])
-def test_cuda_matches_golden(name, deterministic):
-    """deterministic=True runs the sort-then-segment scatter, whose saved state is the general
-    layout: the fused op then writes dL/dmask for all P projections and runs the general
-    backward -- the same results through the other path."""
+@pytest.mark.parametrize("variant", ["default", "deterministic", "global_grid", "deterministic_global_grid"])
+def test_cuda_matches_golden(name, variant):
+    """default / deterministic: the plane-local saved state (winner-only backward, dL/dmask built
+    in the ray kernel), with the atomic and with the sort-then-segment plane build.  global_grid:
+    the raw grid in global memory, whose saved state is the general layout -- the fused op then
+    writes dL/dmask for all P projections and runs the general backward: the same results
+    through the other path."""
     import pytorch_unsup_pc_b200 as dpc
     spec, cfg, t, kernel, idx = _case(name, torch.device("cuda:0"))
-    with dpc.options(deterministic=deterministic):
+    with dpc.options(deterministic=variant.startswith("deterministic"),
+                     plane_local=not variant.endswith("global_grid")):
         out, grads = _fused(dpc, cfg, spec, t, kernel, idx)
     assert abs(out["loss"].item() - float(GOLD[name + "/loss"])) <= 1e-5 * abs(float(GOLD[name + "/loss"]))
     assert out["min_loss"].tolist() == GOLD[name + "/min_loss"].tolist()
