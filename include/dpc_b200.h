@@ -412,6 +412,13 @@ DPC_API int dpc_release(void);
  * pc_gauss_kernel_size taps (gauss_kernel.py:5-11) while sigma falls from 3.0 to 0.2 over training
  * (model_pc_to.py:59-63); kernels are instantiated for radii 2 / 5 / 7 / 10 (Z pass also 0). */
 DPC_API int dpc_tap_radius(const float *taps_host, int n);
+/* Process-wide override of that bound (0: every non-zero tap runs; negative: back to the
+ * default / DPC_TAP_EPS).  Set it between calls, not while another thread is launching. */
+DPC_API int dpc_set_tap_truncation(double eps);
+/* Process-wide switch of the programmatic dependent launches of the kernel chain (1: on, the
+ * default; 0: plain stream-ordered launches -- same results bit for bit; negative: back to the
+ * default / DPC_PDL in the environment).  A/B and test helper; not for use inside a capture. */
+DPC_API int dpc_set_programmatic_launch(int on);
 
 /* Measurement helper (bench.py roofline.fp32_frac): one launch of an FFMA2-only kernel -- the
  * packed inner product of the blur kernels without its loads -- of blocks x 256 threads x iters

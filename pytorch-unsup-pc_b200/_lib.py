@@ -92,6 +92,8 @@ SIGNATURES = {
     "dpc_render_loss_slots": [_P, c_int, c_int, c_int],
     "dpc_release": [],
     "dpc_tap_radius": [c_void_p, c_int],
+    "dpc_set_tap_truncation": [ctypes.c_double],
+    "dpc_set_programmatic_launch": [c_int],
     "dpc_fma_rate_probe": [c_int, c_int, c_void_p, c_void_p, c_void_p],
     "dpc_point_cloud_distance": [c_int, c_int] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p],
     "dpc_project_profile": [_P] + [c_void_p] * 5

@@ -31,22 +31,26 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Profiling hook (dpc_project_profile): when set, an event is recorded after
 // every stage of dpc_project_fwd / dpc_project_bwd on the launching stream.
+static int g_pdl_override = -1;       // dpc_set_programmatic_launch(): 0 / 1, or -1 = DPC_PDL / default
 bool pdl_enabled() {
   static const bool on = [] {
     const char *e = getenv("DPC_PDL");
     return e ? atoi(e) != 0 : true;
   }();
-  return on;
+  return g_pdl_override >= 0 ? g_pdl_override != 0 : on;
 }
 
-// DPC_TAP_EPS (env): total tap magnitude effective_radius() may drop (default 1e-7; 0: none)
+// DPC_TAP_EPS (env): total tap magnitude effective_radius() may drop (default 1e-7; 0: none);
+// dpc_set_tap_truncation() overrides it for the process (a negative value: back to the default)
+static float g_tap_eps_override = -1.f;
 float tap_truncation_eps() {
   static const float eps = [] {
     const char *e = getenv("DPC_TAP_EPS");
     const double v = e ? atof(e) : 1e-7;
     return (float)(v < 0 ? 0 : v);
   }();
-  return eps;
+  const float o = g_tap_eps_override;
+  return o >= 0.f ? o : eps;
 }
 
 static thread_local cudaEvent_t *tl_stage_events = nullptr;
@@ -438,6 +442,16 @@ int dpc_project_chunks(const dpc_params *p) {
 }
 
 int dpc_release(void) { return release_pipeline(); }
+
+int dpc_set_programmatic_launch(int on) {
+  g_pdl_override = on < 0 ? -1 : (on != 0);
+  return DPC_OK;
+}
+
+int dpc_set_tap_truncation(double eps) {
+  g_tap_eps_override = eps >= 0.0 ? (float)eps : -1.f;
+  return DPC_OK;
+}
 
 int dpc_tap_radius(const float *taps_host, int n) {
   if (!taps_host || n < 1 || n % 2 == 0) return -1;

@@ -445,10 +445,14 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
       }
       if (DET) {
         // ---- deterministic build: thread lr sums plane row y = h*RH + lr ----
-        // Row (z, y) receives the points of the four base rows (z - dz, y - dy); the walk order
-        // -- dz = 0 then 1, inside it dy = 0 then 1, inside a segment ascending sorted position
-        // (= ascending point index) -- and the weight products are segment_rows_kernel's
-        // (scatter_sorted.cu), so the plane is bit-identical to the stand-alone sorted scatter.
+        // Row (z, y) receives the points of the four base rows (z - dz, y - dy).  Rows (z - dz,
+        // y - 1) and (z - dz, y) are neighbours in the sorted records, so the row's work is two
+        // contiguous runs; the walk order -- dz = 0 then 1, inside a run ascending sorted
+        // position (row y - 1 before row y, ascending point index inside a row) -- and the weight
+        // products are segment_rows_kernel's (scatter_sorted.cu), so the plane is bit-identical
+        // to the stand-alone sorted scatter.  ONE flat loop over both runs: the trip counts of a
+        // warp's 32 rows differ, and four separate loops cost four times the divergence (ncu:
+        // 48 % of the kernel's warp instructions at 7 active lanes).
         if (tid < C::RH) {
           const int lr = tid, y = h * C::RH + lr;
           if (C::RH != V) {         // several rounds per plane: the bounds of this round's row
@@ -465,37 +469,28 @@ blur_xy_kernel(const float *__restrict__ src, float *__restrict__ dst,
           float *rowp = reinterpret_cast<float *>(A2 + (lr % HALF) * C::S + R) + lr / HALF;
           uint32_t *rbits = sbits + lr * (V / 32);
           const uint4 *sr = cells.srec + (size_t)pb * N;
-          // first record of every segment in flight before the first add
-          uint4 head[2][2];
-#pragma unroll
-          for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-              const uint32_t i0 = seg[dz][1 - dy], i1 = seg[dz][2 - dy];
-              head[dz][dy] = i0 < i1 ? ld_dep(sr + i0) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t a0 = seg[0][0], a1 = seg[0][1], na = seg[0][2] - a0;
+          const uint32_t b0 = seg[1][0], b1 = seg[1][1], total = na + (seg[1][2] - b0);
+          uint4 nxt = total ? ld_dep(sr + (na ? a0 : b0)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+          for (uint32_t t = 0; t < total; ++t) {
+            const uint4 r = nxt;
+            const bool dz = t >= na;
+            const uint32_t i = dz ? b0 + (t - na) : a0 + t;
+            if (t + 1 < total) nxt = ld_dep(sr + (t + 1 >= na ? b0 + (t + 1 - na) : a0 + t + 1));
+            const bool dy = i < (dz ? b1 : a1);       // the run's first row is y - 1
+            const int ix = (int)(r.x & 0xFFu);
+            const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
+            const float wzy = (dz ? rz : 1.f - rz) * (dy ? ry : 1.f - ry);
+            float nv = fmaf(wzy, 1.f - rx, rowp[2 * ix]);
+            rowp[2 * ix] = nv;
+            if (nv > 1.f) rbits[ix >> 5] &= ~(1u << (ix & 31));
+            if (ix + 1 < V) {
+              nv = fmaf(wzy, rx, rowp[2 * ix + 2]);
+              rowp[2 * ix + 2] = nv;
+              if (nv > 1.f) rbits[(ix + 1) >> 5] &= ~(1u << ((ix + 1) & 31));
             }
-#pragma unroll
-          for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-              const uint32_t i0 = seg[dz][1 - dy], i1 = seg[dz][2 - dy];
-              uint4 nxt = head[dz][dy];
-              for (uint32_t i = i0; i < i1; ++i) {
-                const uint4 r = nxt;
-                if (i + 1 < i1) nxt = ld_dep(sr + i + 1);
-                const int ix = (int)(r.x & 0xFFu);
-                const float rz = __uint_as_float(r.y), ry = __uint_as_float(r.z), rx = __uint_as_float(r.w);
-                const float wzy = (dz ? rz : 1.f - rz) * (dy ? ry : 1.f - ry);
-                float nv = fmaf(wzy, 1.f - rx, rowp[2 * ix]);
-                rowp[2 * ix] = nv;
-                if (nv > 1.f) rbits[ix >> 5] &= ~(1u << (ix & 31));
-                if (ix + 1 < V) {
-                  nv = fmaf(wzy, rx, rowp[2 * ix + 2]);
-                  rowp[2 * ix + 2] = nv;
-                  if (nv > 1.f) rbits[(ix + 1) >> 5] &= ~(1u << ((ix + 1) & 31));
-                }
-              }
-            }
+          }
         }
       }
       auto scatter_point = [&](const uint4 r, int dz) {

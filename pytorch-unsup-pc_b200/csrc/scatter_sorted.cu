@@ -16,7 +16,8 @@
 //     once, here.
 //  2. segment_rows_kernel (one thread per output grid row): the row (z, y)
 //     receives contributions only from the four base rows (z-dz, y-dy); the
-//     thread walks those four sorted segments in a fixed order -- segment
+//     thread walks those four sorted segments in a fixed order (dz = 0 then 1, inside it row
+//     y - 1 then row y: ascending sorted position) -- segment
 //     bounds from the table, weights from the records: no pose, no search --
 //     and sums into a private shared-memory row, which the CTA then stores
 //     coalesced.  Every voxel is written exactly once (no memset, no atomics)
@@ -130,19 +131,99 @@ sort_items_kernel(PointSource src, float *__restrict__ tr_out, void *ws, size_t 
 // One CTA per projection: the items are sorted in SHARED memory when the cloud fits (SMEM; else in
 // the two global buffers), and the start of every grid row's segment is tabulated, so that the
 // last kernel neither recomputes a pose nor searches.
+//
+// Fast path (the row table fits the counter region: bins >= rows + 2): ONE counting pass over the
+// full row key -- histogram (shared-memory atomics: counts do not depend on the order), exclusive
+// scan (= the row-segment table), placement through per-row cursors (atomics again: the order
+// INSIDE a row is arbitrary at this point), then every row's handful of items is put into
+// ascending point order by an insertion sort (a thread per row).  The result is THE stable sort
+// -- key ascending, point index ascending -- whatever order the atomics ran in, so it is the
+// 4-pass radix sort's result bit for bit, at a quarter of its passes.  A row that holds more than
+// kRowSortMax points (a degenerate cloud piled into one grid row) sends the projection down the
+// radix path below instead.
+#ifndef DPC_SORT_FAST
+#define DPC_SORT_FAST 1        // A/B: 0 = always the 4-pass radix sort
+#endif
+constexpr uint32_t kRowSortMax = 32;
+constexpr int kSortBinsMax = 20480;      // counter-region words the fast path may ask for (80 KB)
+static int sort_counter_words(int rows) {
+  const int need = (rows + 2 + 3) & ~3;
+  return (DPC_SORT_FAST && need <= kSortBinsMax && need > 16 * kSortThreads) ? need : 16 * kSortThreads;
+}
 template <bool SMEM, bool CELLS>
 __global__ void __launch_bounds__(kSortThreads)
-sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cells) {
-  extern __shared__ uint32_t sm_sort[];           // cnt [16 * threads] | SMEM: A [N] | B [N]
+sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cells, int cnt_words) {
+  extern __shared__ uint32_t sm_sort[];           // cnt [cnt_words] | SMEM: A [N] | B [N]
   __shared__ uint32_t warp_tot[kSortThreads / 32];
-  uint32_t *cnt = sm_sort, *sm_items = sm_sort + 16 * kSortThreads;
+  uint32_t *cnt = sm_sort, *sm_items = sm_sort + cnt_words;
   const int b = blockIdx.x, tid = threadIdx.x;
   const SortedView sv = sorted_view(ws, stride, b, N);
   uint32_t *A = SMEM ? sm_items : sv.A, *B = SMEM ? sm_items + N : sv.B;
   const uint32_t rows = (uint32_t)(Vz * V);       // the key of out-of-frustum points
+  uint32_t *bs = CELLS ? cells.binstart + (size_t)b * cells.zstride : nullptr;
   if (SMEM)
     for (int n = tid; n < N; n += kSortThreads) A[n] = sv.A[n];
-  __syncthreads();
+  const uint32_t *sorted = A;                     // where the sorted items end up
+  bool table_done = false;                        // rowstart (and binstart) already written
+  const int nb = (int)rows + 2;                   // bins: rows, the out-of-frustum key, a zero
+  if (DPC_SORT_FAST && nb <= cnt_words) {
+    uint32_t *bins = cnt;
+    for (int k = tid; k < nb; k += kSortThreads) bins[k] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += kSortThreads) atomicAdd(&bins[A[i] >> 16], 1u);
+    __syncthreads();
+    // exclusive scan: a contiguous chunk of bins per thread, warp scan, warp totals
+    const int per = (nb + kSortThreads - 1) / kSortThreads;
+    const int k0 = min(tid * per, nb), k1 = min(k0 + per, nb);
+    uint32_t sum = 0;
+    bool big = false;
+    for (int k = k0; k < k1; ++k) {
+      const uint32_t v = bins[k];
+      sum += v;
+      big |= (uint32_t)k < rows && v > kRowSortMax;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    if (!__syncthreads_or(big)) {
+      uint32_t run = incl - sum;
+      for (int w = 0; w < (tid >> 5); ++w) run += warp_tot[w];
+      for (int k = k0; k < k1; ++k) {
+        const uint32_t v = bins[k];
+        bins[k] = run;                              // the row's cursor
+        sv.rowstart[k] = run;                       // rowstart[rows] = valid points, [rows + 1] = N
+        if (CELLS && (uint32_t)k <= rows && (uint32_t)k % (uint32_t)V == 0) bs[(uint32_t)k / (uint32_t)V] = run;
+        run += v;
+      }
+      __syncthreads();
+      for (int i = tid; i < N; i += kSortThreads) {
+        const uint32_t item = A[i];
+        B[atomicAdd(&bins[item >> 16], 1u)] = item;
+      }
+      __syncthreads();
+      // bins[k] is now the END of row k: ascending point index inside every row (the
+      // out-of-frustum tail keeps its arbitrary order: nobody reads those records)
+      for (uint32_t k = tid; k < rows; k += kSortThreads) {
+        const uint32_t s0 = k ? bins[k - 1] : 0u, s1 = bins[k];
+        for (uint32_t i = s0 + 1; i < s1; ++i) {
+          const uint32_t item = B[i];
+          uint32_t j = i;
+          for (; j > s0 && B[j - 1] > item; --j) B[j] = B[j - 1];
+          B[j] = item;
+        }
+      }
+      sorted = B;
+      table_done = true;
+    }
+    __syncthreads();
+  } else {
+    __syncthreads();
+  }
+  if (!table_done) {
   // contiguous chunk per thread (stable); an ODD chunk length keeps the threads' walks on
   // different shared-memory banks
   int chunk = (N + kSortThreads - 1) / kSortThreads;
@@ -185,16 +266,18 @@ sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cell
     __syncthreads();
     uint32_t *t = from; from = to; to = t;
   }
-  // 4 passes: the sorted array ends in A.  Segment starts: rowstart[k] = first index whose key
-  // is >= k, for k = 0 .. rows + 1 (rowstart[rows] = the first out-of-frustum point,
-  // rowstart[rows + 1] = N); the sorted items go to the global buffer the second kernel reads
+  }
+  // (radix: 4 passes, the sorted array ends in A.)  Segment starts: rowstart[k] = first index
+  // whose key is >= k, for k = 0 .. rows + 1 (rowstart[rows] = the first out-of-frustum point,
+  // rowstart[rows + 1] = N); the records go to the global buffer the next kernel reads, in
+  // sorted order
   const uint4 *rec = CELLS ? cells.rec + (size_t)b * N : sv.rec;
   uint4 *srec = CELLS ? cells.srec + (size_t)b * N : sv.srec;
-  uint32_t *bs = CELLS ? cells.binstart + (size_t)b * cells.zstride : nullptr;
   for (int i = tid; i < N; i += kSortThreads) {
-    const uint32_t item = A[i], key = item >> 16;
-    srec[i] = rec[item & 0xffffu];                // the records in sorted order: sequential reads later
-    const uint32_t prev = i > 0 ? (A[i - 1] >> 16) + 1u : 0u;
+    const uint32_t item = sorted[i], key = item >> 16;
+    srec[i] = rec[item & 0xffffu];                // sequential reads later
+    if (table_done) continue;
+    const uint32_t prev = i > 0 ? (sorted[i - 1] >> 16) + 1u : 0u;
     for (uint32_t k = prev; k <= key; ++k) {
       sv.rowstart[k] = (uint32_t)i;
       // rows are z-major: the first row of a z cell starts the cell (k == rows: the valid total)
@@ -222,7 +305,7 @@ segment_rows_kernel(const void *ws, size_t stride, int N, int Vz, int V, float *
 #pragma unroll
     for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
+      for (int dy = 1; dy >= 0; --dy) {         // ascending sorted position: row oy - 1, then row oy
         const int bz = oz - dz, by = oy - dy;
         if (bz < 0 || by < 0) continue;
         const int key = bz * V + by;
@@ -282,23 +365,23 @@ static int launch_sort(const PoseArgs *a, const float *tr_pc_in, int P, int N, i
     sort_items_kernel<false><<<gi, kItemThreads, 0, s>>>(src, a ? tr_pc_out : nullptr, ws, stride,
                                                          N, Vz, V, cv);
   if (int e = check_launch("sort_items")) return e;
-  const size_t cnt_smem = (size_t)16 * kSortThreads * sizeof(uint32_t);
+  const int cnt_words = sort_counter_words(Vz * V);
+  const size_t cnt_smem = (size_t)cnt_words * sizeof(uint32_t);
   static DeviceOnce sort_once;
   if (sort_once.first()) {
-    const int big = (int)cnt_smem + 2 * kSmemSortMax * (int)sizeof(uint32_t);
+    const int small = kSortBinsMax * (int)sizeof(uint32_t);
+    const int big = small + 2 * kSmemSortMax * (int)sizeof(uint32_t);
     cudaFuncSetAttribute(sort_points_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(sort_points_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(sort_points_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)cnt_smem);
-    cudaFuncSetAttribute(sort_points_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)cnt_smem);
+    cudaFuncSetAttribute(sort_points_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    cudaFuncSetAttribute(sort_points_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
   }
   const bool in_smem = N <= kSmemSortMax;
   const size_t smem = cnt_smem + (in_smem ? (size_t)2 * N * sizeof(uint32_t) : 0);
-  if (in_smem && cells) sort_points_kernel<true, true><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
-  else if (in_smem) sort_points_kernel<true, false><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
-  else if (cells) sort_points_kernel<false, true><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
-  else sort_points_kernel<false, false><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv);
+  if (in_smem && cells) sort_points_kernel<true, true><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv, cnt_words);
+  else if (in_smem) sort_points_kernel<true, false><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv, cnt_words);
+  else if (cells) sort_points_kernel<false, true><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv, cnt_words);
+  else sort_points_kernel<false, false><<<P, kSortThreads, smem, s>>>(ws, stride, N, Vz, V, cv, cnt_words);
   return check_launch("sort_points");
 }
 

@@ -1,8 +1,10 @@
 """Per-stage CUDA-event timings of one projection step through dpc_project_profile (dev helper
 for kernel A/B runs: DPC_B200_LIB=<variant .so> python scripts/stage_time.py [A|B] [iters] [box]).
 `box` < 0.9 shrinks the synthetic clouds to a cube of that side (an object that fills part of
-the frustum: planes of depth no point touches)."""
+the frustum: planes of depth no point touches).  DPC_STAGE_SORTED=1 runs the deterministic
+(sort-then-segment) mode; the printed digest covers every output and gradient bit for bit."""
 import ctypes
+import hashlib
 import os
 import sys
 
@@ -38,10 +40,11 @@ def main(workload="A", iters=30, box=0.9, P=0):
     sptr = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     P_ = ops._ptr
     stage_ms = (ctypes.c_float * len(_lib.PROFILE_STAGES))()
+    mode = _lib.SCATTER_SORTED if os.environ.get("DPC_STAGE_SORTED") else _lib.SCATTER_ATOMIC
     for it in (3, iters):
         st = lib.dpc_project_profile(
             ctypes.byref(params), P_(d["points"]), P_(d["quat"]), None, None, P_(d["scale"]),
-            *ops._tap_args(taps), _lib.SCATTER_ATOMIC, P_(buf["tr_pc"]), P_(buf["grid"]), P_(buf["bits"]),
+            *ops._tap_args(taps), mode, P_(buf["tr_pc"]), P_(buf["grid"]), P_(buf["bits"]),
             P_(buf["cells"]), P_(buf["mask"]), P_(buf["depth"]), P_(d["g_mask"]), P_(d["g_depth"]),
             P_(buf["g_grid"]), P_(buf["g_points"]), P_(buf["g_quat"]), None, None, P_(buf["g_scale"]),
             P_(ws), ws.numel(), sptr, it, stage_ms)
@@ -49,8 +52,11 @@ def main(workload="A", iters=30, box=0.9, P=0):
     torch.cuda.synchronize()
     t = {k: round(float(v) * 1e3, 1) for k, v in zip(_lib.PROFILE_STAGES, stage_ms)}
     chk = [float(buf[k].double().abs().sum()) for k in ("mask", "depth", "g_points", "g_quat", "g_scale")]
-    print(os.path.basename(_lib.LIB_PATH), workload, "P", P, "box %.2f" % box, t, "sum %.1f" % sum(t.values()),
-          "chk", " ".join("%.6e" % c for c in chk))
+    h = hashlib.sha256()
+    for k in ("tr_pc", "mask", "depth", "g_points", "g_quat", "g_scale"):
+        h.update(buf[k].cpu().numpy().tobytes())
+    print(os.path.basename(_lib.LIB_PATH), workload, "sorted" if mode else "atomic", "P", P, "box %.2f" % box, t,
+          "sum %.1f" % sum(t.values()), "chk", " ".join("%.6e" % c for c in chk), "sha", h.hexdigest()[:16])
 
 
 if __name__ == "__main__":

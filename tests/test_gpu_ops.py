@@ -133,31 +133,29 @@ def test_no_cpu_fallback(dpc):
 
 
 def test_plain_launches_give_the_same_bits(dpc):
-    """DPC_PDL=0 (read once per process) launches the chain's kernels as plain stream-ordered
-    kernels instead of programmatic dependent launches: a fresh process computes one projection
-    step both ways and the outputs and gradients must be the same bits."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import sys, torch; sys.path.insert(0, %r)\n"
-        "import pytorch_unsup_pc_b200 as dpc\n"
-        "cfg = dpc.default_cfg(vox_size=64, pc_gauss_kernel_size=21)\n"
-        "g = torch.Generator().manual_seed(77)\n"
-        "p = ((torch.rand(66, 3000, 3, generator=g) - 0.5) * 0.9).cuda().requires_grad_()\n"
-        "q = torch.randn(66, 4, generator=g).cuda().requires_grad_()\n"
-        "o = dpc.pointcloud_project_fast(cfg, p, q, None, None, dpc.smoothing_kernel(cfg, 3.0))\n"
-        "gp, gq = torch.autograd.grad(o['proj'].sum() + o['proj_depth'].sum(), [p, q])\n"
-        "print(' '.join(repr(float(t.double().sum())) for t in (o['proj'], o['proj_depth'], gp, gq)))\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    """dpc_set_programmatic_launch(0) launches the chain's kernels as plain stream-ordered kernels
+    instead of programmatic dependent launches: one projection step (66 projections: the two
+    half-batch chains on the internal streams) both ways, and every output and gradient must be
+    the same bits."""
+    lib = dpc._lib.load()
+    cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
+    g = torch.Generator().manual_seed(77)
+    pts = ((torch.rand(66, 3000, 3, generator=g) - 0.5) * 0.9).to(DEV)
+    quat = torch.randn(66, 4, generator=g).to(DEV)
+    kern = dpc.smoothing_kernel(cfg, 3.0)
     outs = []
-    for pdl in ("1", "0"):
-        env = dict(os.environ, DPC_PDL=pdl)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
-                           timeout=300)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(r.stdout.strip().splitlines()[-1])
-    assert outs[0] == outs[1], outs
+    for pdl in (1, 0):
+        lib.dpc_set_programmatic_launch(pdl)
+        try:
+            p, q = pts.clone().requires_grad_(), quat.clone().requires_grad_()
+            o = dpc.pointcloud_project_fast(cfg, p, q, None, None, kern)
+            gp, gq = torch.autograd.grad(o["proj"].sum() + o["proj_depth"].sum(), [p, q])
+            torch.cuda.synchronize()
+        finally:
+            lib.dpc_set_programmatic_launch(-1)
+        outs.append((o["proj"], o["proj_depth"], o["voxels"], o["drc_probs"], o["tr_pc"], gp, gq))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
 
 
 def test_full_size_properties(dpc):

@@ -104,75 +104,57 @@ def test_thin_slab_leaves_most_planes_empty(dpc, V, outputs):
 
 
 SIGMAS = (3.0, 2.0, 1.3, 1.0, 0.8, 0.6, 0.4, 0.2)
-_FULL_TAPS_SCRIPT = r"""
-import sys, numpy as np, torch
-sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-import _inputs
-import pytorch_unsup_pc_b200 as dpc
-from oracle import closed_form as CF
-from oracle.config import default_cfg
-cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
-dev = torch.device("cuda:0")
-out = {{}}
-for sigma in {sigmas!r}:
-    case = _inputs.make_case(cfg, 3, 3000, 600 + int(10 * sigma), scale=True, screened=True)
+
+
+def _run_schedule_case(dpc, cfg, case, kern, dev):
     leaves = [case[k].to(dev).requires_grad_() for k in ("points", "quat", "scale")]
     dpc.set_outputs(voxels=False, drc_probs=False)
-    o = dpc.pointcloud_project_fast(cfg, leaves[0], leaves[1], None, None, CF.smoothing_taps(cfg, sigma),
-                                    scaling_factor=leaves[2])
-    Wp, Wd = (w.to(dev) for w in _inputs.loss_weights(3, 64))
-    g = torch.autograd.grad((o["proj"] * Wp).sum() + 0.1 * (o["proj_depth"] * Wd).sum(), leaves)
-    for k, v in zip(("proj", "depth", "g_points", "g_quat", "g_scale"), (o["proj"], o["proj_depth"]) + g):
-        out["%s/%s" % (sigma, k)] = v.detach().cpu().numpy()
-np.savez({path!r}, **out)
-"""
+    try:
+        o = dpc.pointcloud_project_fast(cfg, leaves[0], leaves[1], None, None, kern,
+                                        scaling_factor=leaves[2])
+    finally:
+        dpc.set_outputs(voxels=True, drc_probs=True)
+    Wp, Wd = _inputs.loss_weights(3, 64)
+    g = torch.autograd.grad((o["proj"] * Wp.to(dev)).sum() + 0.1 * (o["proj_depth"] * Wd.to(dev)).sum(), leaves)
+    return dict(zip(("proj", "depth", "g_points", "g_quat", "g_scale"), (o["proj"], o["proj_depth"]) + g))
 
 
-def test_sigma_schedule_tap_truncation(tmp_path):
+def test_sigma_schedule_tap_truncation():
     """sigma_rel runs 3.0 -> 0.2 over training (model_pc_to.py:59-63) with K = 21 taps throughout;
     the kernels run with the radius that holds all but 1e-7 of the taps (dpc_tap_radius: 10, 10,
     8, 6, 5, 4, 2, 1 for these sigmas -> templates 10 / 7 / 5 / 2), taps not re-normalised.
     Against the oracle (all 21 taps, fp64): the usual 1e-5 / 1e-4.  Against the same kernels run
-    with every tap (DPC_TAP_EPS=0, in a subprocess: the setting is read once per process):
-    within 1e-6 forward, 1e-5 on the gradients."""
-    import os
-    import subprocess
-    import sys
-    import numpy as np
+    with every non-zero tap (dpc_set_tap_truncation(0)): within 1e-6 forward, 1e-5 on the
+    gradients."""
     import pytorch_unsup_pc_b200 as dpc
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    path = str(tmp_path / "full_taps.npz")
-    env = dict(os.environ, DPC_TAP_EPS="0")
-    res = subprocess.run([sys.executable, "-c", _FULL_TAPS_SCRIPT.format(
-        root=root, tests=os.path.join(root, "tests"), sigmas=SIGMAS, path=path)],
-        env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stderr[-2000:]
-    full = dict(np.load(path))
     cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=21)
     dev = torch.device("cuda:0")
     lib = dpc._lib.load()
+    radii = []
     for sigma in SIGMAS:
         case = _inputs.make_case(cfg, 3, 3000, 600 + int(10 * sigma), scale=True, screened=True)
         kern = CF.smoothing_taps(cfg, sigma)
-        leaves = [case[k].to(dev).requires_grad_() for k in ("points", "quat", "scale")]
-        dpc.set_outputs(voxels=False, drc_probs=False)
+        taps = kern[0].reshape(-1).contiguous()
+        lib.dpc_set_tap_truncation(0.0)
         try:
-            o = dpc.pointcloud_project_fast(cfg, leaves[0], leaves[1], None, None, kern,
-                                            scaling_factor=leaves[2])
+            nz = torch.nonzero(taps).reshape(-1)          # (taps that underflowed to 0.0f never run)
+            assert lib.dpc_tap_radius(taps.data_ptr(), taps.numel()) == int(nz.max()) - 10
+            full = _run_schedule_case(dpc, cfg, case, kern, dev)
         finally:
-            dpc.set_outputs(voxels=True, drc_probs=True)
-        Wp, Wd = _inputs.loss_weights(3, 64)
-        g = torch.autograd.grad((o["proj"] * Wp.to(dev)).sum() + 0.1 * (o["proj_depth"] * Wd.to(dev)).sum(), leaves)
-        got = dict(zip(("proj", "depth", "g_points", "g_quat", "g_scale"), (o["proj"], o["proj_depth"]) + g))
+            lib.dpc_set_tap_truncation(-1.0)
+        got = _run_schedule_case(dpc, cfg, case, kern, dev)
         ol = [case[k].clone().requires_grad_() for k in ("points", "quat", "scale")]
         ref = CF.project(cfg, ol[0], ol[1], None, kern, ol[2])
+        Wp, Wd = _inputs.loss_weights(3, 64)
         rg = torch.autograd.grad((ref["proj"] * Wp.double()).sum() + 0.1 * (ref["proj_depth"] * Wd.double()).sum(), ol)
         want = dict(zip(("proj", "depth", "g_points", "g_quat", "g_scale"), (ref["proj"], ref["proj_depth"]) + rg))
-        taps = kern[0].reshape(-1).contiguous()
         r = lib.dpc_tap_radius(taps.data_ptr(), taps.numel())
+        radii.append(r)
         for k in got:
             tol = 1e-5 if k in ("proj", "depth") else 1e-4
             e_or = _golden.rel_err(got[k].reshape(want[k].shape), want[k])
-            e_full = _golden.rel_err(got[k], full["%s/%s" % (sigma, k)])
+            e_full = _golden.rel_err(got[k], full[k])
             assert e_or < tol, (sigma, r, k, e_or)
             assert e_full < tol / 10, (sigma, r, k, e_full)
+    assert radii[0] == 10 and radii[-1] <= 2 and sorted(radii, reverse=True) == radii, radii
+
