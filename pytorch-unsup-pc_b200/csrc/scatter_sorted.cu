@@ -271,12 +271,29 @@ sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cell
   // whose key is >= k, for k = 0 .. rows + 1 (rowstart[rows] = the first out-of-frustum point,
   // rowstart[rows + 1] = N); the records go to the global buffer the next kernel reads, in
   // sorted order
-  const uint4 *rec = CELLS ? cells.rec + (size_t)b * N : sv.rec;
-  uint4 *srec = CELLS ? cells.srec + (size_t)b * N : sv.srec;
+  const uint4 *__restrict__ rec = CELLS ? cells.rec + (size_t)b * N : sv.rec;
+  uint4 *__restrict__ srec = CELLS ? cells.srec + (size_t)b * N : sv.srec;
+  if (table_done) {
+    // (nothing but the gather: unrolled, so that a thread's loads are in flight together)
+    constexpr int G = 4;
+    for (int i0 = tid; i0 < N; i0 += G * kSortThreads) {
+      uint4 r[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int i = i0 + g * kSortThreads;
+        if (i < N) r[g] = __ldcg(rec + (sorted[i] & 0xffffu));
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int i = i0 + g * kSortThreads;
+        if (i < N) srec[i] = r[g];
+      }
+    }
+    return;
+  }
   for (int i = tid; i < N; i += kSortThreads) {
     const uint32_t item = sorted[i], key = item >> 16;
     srec[i] = rec[item & 0xffffu];                // sequential reads later
-    if (table_done) continue;
     const uint32_t prev = i > 0 ? (sorted[i - 1] >> 16) + 1u : 0u;
     for (uint32_t k = prev; k <= key; ++k) {
       sv.rowstart[k] = (uint32_t)i;
