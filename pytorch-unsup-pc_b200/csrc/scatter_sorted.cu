@@ -135,16 +135,16 @@ sort_items_kernel(PointSource src, float *__restrict__ tr_out, void *ws, size_t 
 // Fast path (the row table fits the counter region: bins >= rows + 2): ONE counting pass over the
 // full row key -- histogram (shared-memory atomics: counts do not depend on the order), exclusive
 // scan (= the row-segment table), placement through per-row cursors (atomics again: the order
-// INSIDE a row is arbitrary at this point), then every row's handful of items is put into
-// ascending point order by an insertion sort (a thread per row).  The result is THE stable sort
-// -- key ascending, point index ascending -- whatever order the atomics ran in, so it is the
-// 4-pass radix sort's result bit for bit, at a quarter of its passes.  A row that holds more than
-// kRowSortMax points (a degenerate cloud piled into one grid row) sends the projection down the
-// radix path below instead.
+// INSIDE a row is arbitrary at this point), then every item is ranked inside its row by counting
+// the row's smaller items (a row holds a handful) and its record is written to that place.  The
+// result is THE stable sort -- key ascending, point index ascending -- whatever order the atomics
+// ran in, so it is the 4-pass radix sort's result bit for bit, at a quarter of its passes.  A row
+// that holds more than kRowSortMax points (a degenerate cloud piled into one grid row: the
+// ranking is quadratic in the row) sends the projection down the radix path below instead.
 #ifndef DPC_SORT_FAST
 #define DPC_SORT_FAST 1        // A/B: 0 = always the 4-pass radix sort
 #endif
-constexpr uint32_t kRowSortMax = 32;
+constexpr uint32_t kRowSortMax = 128;
 constexpr int kSortBinsMax = 20480;      // counter-region words the fast path may ask for (80 KB)
 static int sort_counter_words(int rows) {
   const int need = (rows + 2 + 3) & ~3;
@@ -163,8 +163,6 @@ sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cell
   uint32_t *bs = CELLS ? cells.binstart + (size_t)b * cells.zstride : nullptr;
   if (SMEM)
     for (int n = tid; n < N; n += kSortThreads) A[n] = sv.A[n];
-  const uint32_t *sorted = A;                     // where the sorted items end up
-  bool table_done = false;                        // rowstart (and binstart) already written
   const int nb = (int)rows + 2;                   // bins: rows, the out-of-frustum key, a zero
   if (DPC_SORT_FAST && nb <= cnt_words) {
     uint32_t *bins = cnt;
@@ -205,25 +203,48 @@ sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cell
         B[atomicAdd(&bins[item >> 16], 1u)] = item;
       }
       __syncthreads();
-      // bins[k] is now the END of row k: ascending point index inside every row (the
-      // out-of-frustum tail keeps its arbitrary order: nobody reads those records)
-      for (uint32_t k = tid; k < rows; k += kSortThreads) {
-        const uint32_t s0 = k ? bins[k - 1] : 0u, s1 = bins[k];
-        for (uint32_t i = s0 + 1; i < s1; ++i) {
-          const uint32_t item = B[i];
-          uint32_t j = i;
-          for (; j > s0 && B[j - 1] > item; --j) B[j] = B[j - 1];
-          B[j] = item;
+      // bins[k] is now the END of row k.  Every item finds its place inside its row by counting
+      // the row's smaller items (a row holds a handful; the items are distinct) -- item-parallel,
+      // so lanes do not wait for the longest row of the warp as a sort per row made them (ncu:
+      // 40 % of the kernel's warp instructions at 7 active lanes) -- and its record goes straight
+      // to that place: the record loads, random 16-byte reads from L2, are all requested before
+      // the first count.  (The out-of-frustum tail keeps its arbitrary order: nobody reads it.)
+      {
+        const uint4 *__restrict__ rec = CELLS ? cells.rec + (size_t)b * N : sv.rec;
+        uint4 *__restrict__ srec = CELLS ? cells.srec + (size_t)b * N : sv.srec;
+        constexpr int G = 4;
+        for (int i0 = tid; i0 < N; i0 += G * kSortThreads) {
+          uint32_t item[G];
+          uint4 r[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int i = i0 + g * kSortThreads;
+            item[g] = i < N ? B[i] : 0xffffffffu;
+            if (i < N) r[g] = __ldcg(rec + (item[g] & 0xffffu));
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int i = i0 + g * kSortThreads;
+            if (i >= N) continue;
+            const uint32_t key = item[g] >> 16;
+            uint32_t pos = (uint32_t)i;
+            if (key < rows) {
+              const uint32_t s0 = key ? bins[key - 1] : 0u, s1 = bins[key];
+              pos = s0;
+              for (uint32_t j = s0; j < s1; ++j) pos += B[j] < item[g] ? 1u : 0u;
+            }
+            srec[pos] = r[g];
+          }
         }
       }
-      sorted = B;
-      table_done = true;
+      return;
     }
     __syncthreads();
   } else {
     __syncthreads();
   }
-  if (!table_done) {
+  // ---- the stable 4-pass LSD radix sort (grids whose row table does not fit, piled-up rows) ----
+  {
   // contiguous chunk per thread (stable); an ODD chunk length keeps the threads' walks on
   // different shared-memory banks
   int chunk = (N + kSortThreads - 1) / kSortThreads;
@@ -273,28 +294,10 @@ sort_points_kernel(void *ws, size_t stride, int N, int Vz, int V, CellsView cell
   // sorted order
   const uint4 *__restrict__ rec = CELLS ? cells.rec + (size_t)b * N : sv.rec;
   uint4 *__restrict__ srec = CELLS ? cells.srec + (size_t)b * N : sv.srec;
-  if (table_done) {
-    // (nothing but the gather: unrolled, so that a thread's loads are in flight together)
-    constexpr int G = 4;
-    for (int i0 = tid; i0 < N; i0 += G * kSortThreads) {
-      uint4 r[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int i = i0 + g * kSortThreads;
-        if (i < N) r[g] = __ldcg(rec + (sorted[i] & 0xffffu));
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int i = i0 + g * kSortThreads;
-        if (i < N) srec[i] = r[g];
-      }
-    }
-    return;
-  }
   for (int i = tid; i < N; i += kSortThreads) {
-    const uint32_t item = sorted[i], key = item >> 16;
+    const uint32_t item = A[i], key = item >> 16;
     srec[i] = rec[item & 0xffffu];                // sequential reads later
-    const uint32_t prev = i > 0 ? (sorted[i - 1] >> 16) + 1u : 0u;
+    const uint32_t prev = i > 0 ? (A[i - 1] >> 16) + 1u : 0u;
     for (uint32_t k = prev; k <= key; ++k) {
       sv.rowstart[k] = (uint32_t)i;
       // rows are z-major: the first row of a z cell starts the cell (k == rows: the valid total)
