@@ -16,7 +16,10 @@ torch.cuda.set_device(lr)
 args = argparse.Namespace(steps=40, warmup=5)
 env = bench.Env(args, rank, world, lr)
 if world > 1:
-    dist.init_process_group("nccl", device_id=env.dev)
+    opts = None
+    if os.environ.get("DPC_NCCL_HIGH_PRIORITY"):
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", device_id=env.dev, pg_options=opts)
 rec = train_step.bench(env, args)
 env.fence()
 if world > 1:
