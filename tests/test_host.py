@@ -139,6 +139,20 @@ def test_tap_radius_follows_sigma():
     one = torch.ones(1)
     assert lib.dpc_tap_radius(one.data_ptr(), 1) == 0
     assert lib.dpc_tap_radius(one.data_ptr(), 2) == -1
+    # the run-time override (what the sigma-schedule GPU test uses instead of a child process):
+    # 0 keeps every non-zero tap, a larger bound drops more, a negative value restores the default
+    taps = dpc.smoothing_kernel(cfg, 1.0)[0].reshape(-1).contiguous()
+    try:
+        assert lib.dpc_set_tap_truncation(0.0) == 0
+        nz = torch.nonzero(taps).reshape(-1)
+        assert lib.dpc_tap_radius(taps.data_ptr(), taps.numel()) == int(nz.max()) - 10 == 10
+        assert lib.dpc_set_tap_truncation(1e-3) == 0
+        assert lib.dpc_tap_radius(taps.data_ptr(), taps.numel()) < got[1.0]
+    finally:
+        lib.dpc_set_tap_truncation(-1.0)
+    assert lib.dpc_tap_radius(taps.data_ptr(), taps.numel()) == got[1.0]
+    # (the launch-mode switch is a plain setter; its effect is covered on the GPU)
+    assert lib.dpc_set_programmatic_launch(0) == 0 and lib.dpc_set_programmatic_launch(-1) == 0
 
 
 def test_render_loss_argument_validation_needs_no_gpu():
