@@ -180,3 +180,92 @@ def ref_project_replicated(cfg, point_cloud, transform, step_size, num_candidate
     out = ref_project(cfg, pts, transform, predicted_translation, kernel, scaling_factor,
                       focal_length)
     return out, indices
+
+
+# ---------------------------------------------------------------------------------------------
+# The point-feature (RGB) branch: the reference's TensorFlow original, executed through
+# oracle/tf_shim.py
+# ---------------------------------------------------------------------------------------------
+_tf_pc = None
+
+
+def load_tf_point_cloud():
+    """Import the reference's TF original ``util/point_cloud.py`` UNMODIFIED with
+    ``oracle.tf_shim`` standing in for ``tensorflow``.  What it imports next to TensorFlow
+    (``util.drc``, ``util.quaternion``, ``util.camera``, ``util.point_cloud_distance``) are the
+    reference's own torch / numpy files, so poses and ray probabilities are computed by exactly
+    the code ``ref_project`` runs."""
+    global _tf_pc
+    if _tf_pc is not None:
+        return _tf_pc
+    load()
+    import importlib
+    from . import tf_shim
+    had = sys.modules.get("tensorflow")
+    sys.modules["tensorflow"] = tf_shim
+    try:
+        _tf_pc = importlib.import_module("util.point_cloud")
+    finally:
+        if had is None:
+            del sys.modules["tensorflow"]
+        else:
+            sys.modules["tensorflow"] = had
+    return _tf_pc
+
+
+class _TorchWithTyposRepaired:
+    """Stands in for the name ``torch`` inside the reference's util/drc.py while its
+    ``project_volume_rgb_integral`` (drc.py:132-142) runs: ``torch.float63`` (:137) reads as
+    float64 and ``torch.ones(shape=...)`` (:137) as ``torch.ones(size=...)``.  Everything else is
+    torch itself; no reference line is copied or edited."""
+    float63 = torch.float64
+
+    @staticmethod
+    def ones(*args, shape=None, **kw):
+        return torch.ones(*args, **kw) if shape is None else torch.ones(tuple(shape), **kw)
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+
+@contextlib.contextmanager
+def _rgb_integral_runnable(drc):
+    """util/point_cloud.py:277 hands ``project_volume_rgb_integral`` the TF layout
+    [B,Z,Y,X,C]; the function's torch port (the only version in the tree) swaps axes for the
+    torch port's channel-first layout [B,C,Z,Y,X] (drc.py:134, fed by point_cloud_to.py:113).
+    Hand it that layout and let its own lines run, with the two typos of :137 repaired."""
+    orig_fn, orig_torch = drc.project_volume_rgb_integral, drc.torch
+
+    def call(cfg, p, rgb):
+        return orig_fn(cfg, p, rgb.permute(0, 4, 1, 2, 3))
+
+    drc.project_volume_rgb_integral, drc.torch = call, _TorchWithTyposRepaired()
+    try:
+        yield
+    finally:
+        drc.project_volume_rgb_integral, drc.torch = orig_fn, orig_torch
+
+
+def tf_kernel(kernel):
+    """The reference's separable blur kernels (torch layout [out,in,kd,kh,kw], gauss_kernel.py)
+    in the layout ``tf.nn.conv3d`` takes: [kd,kh,kw,in,out]."""
+    from . import tf_shim
+    if kernel is None:
+        return None
+    return [tf_shim.wrap(k.permute(2, 3, 4, 1, 0)) for k in kernel]
+
+
+def ref_project_tf(cfg, point_cloud, transform, predicted_translation=None, all_rgb=None,
+                   kernel=None, scaling_factor=None, focal_length=None):
+    """The reference's TF-original ``pointcloud_project_fast`` (util/point_cloud.py:229-290)
+    called as-is through the shim; returns its output dict as plain torch tensors ([B,Z,Y,X,C]
+    grids, [B,Y,X,C] images), still attached to the autograd graph of the arguments."""
+    from . import tf_shim
+    pc = load_tf_point_cloud()
+    drc = load()["drc"]
+    w = tf_shim.wrap
+    with _rgb_integral_runnable(drc):
+        out = pc.pointcloud_project_fast(cfg, w(point_cloud), w(transform), w(predicted_translation),
+                                         w(all_rgb), tf_kernel(kernel), w(scaling_factor),
+                                         w(focal_length))
+    return {k: tf_shim.unwrap(v) for k, v in out.items()}

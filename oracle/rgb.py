@@ -2,10 +2,14 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py) -- never imported by the product.
 
-PARITY UNPINNED.  The reference's torch port of this branch does not run
-(util/point_cloud_to.py:64 ``updates_raw. tf.expand_dims`` AttributeError; util/drc.py:137
-``torch.float63``) and TensorFlow is not installed, so nothing can be executed to pin this
-restatement.  It follows the TF original line by line:
+PINNED against the reference's TensorFlow original.  The reference's torch port of this branch
+does not run (util/point_cloud_to.py:64 ``updates_raw. tf.expand_dims`` AttributeError;
+util/drc.py:137 ``torch.float63``) and TensorFlow is not installed, but the TF original
+(util/point_cloud.py) is complete: ``oracle.ref_loader.ref_project_tf`` executes it UNMODIFIED
+through ``oracle/tf_shim.py`` (a ``tensorflow`` namespace over torch, validated bit for bit against
+the reference's torch port on the occupancy path), and this restatement agrees with it to fp64
+rounding: forward 1e-13, fp64 gradients 1e-10 (tests/test_rgb.py, live and against the
+reference-made fixture tests/golden/rgb_tf.npz).  It follows the TF original line by line:
   * feature scatter                 util/point_cloud.py:99-129   (interpolate_scatter3d)
   * clip before the blur, blur      util/point_cloud.py:244-249, 148-154 (convolve_rgb)
   * division by blurred occupancy   util/point_cloud.py:256-260

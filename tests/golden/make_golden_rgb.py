@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """Generate tests/golden/rgb.npz from oracle/rgb.py:    python tests/golden/make_golden_rgb.py
 
-NOT made by the reference: its torch port of the rgb branch does not run
-(util/point_cloud_to.py:64, util/drc.py:137) and TensorFlow is absent, so these vectors come
-from the oracle's restatement of the TF original (parity unpinned, see oracle/rgb.py).  They
-freeze that restatement -- a regression fixture for the oracle and the CUDA path, no more.
+Made by the ORACLE, not by the reference (its torch port of the rgb branch does not run:
+util/point_cloud_to.py:64, util/drc.py:137): a regression fixture for the oracle's restatement
+and the CUDA path.  The reference-made twin is rgb_tf.npz (make_golden_rgb_tf.py: the
+reference's TF original executed through oracle/tf_shim.py);
+tests/test_rgb.py::test_oracle_made_fixture_equals_reference_made_fixture compares the two entry
+by entry.
 """
 import os
 import sys
