@@ -1032,16 +1032,34 @@ def run_b200(args, rank, world, local_rank):
     if not args.main_only:
         main["trajectory"] = bench_trajectory(env, args.workload if args.workload in ("A", "C3") else "A")
     subs = {}
+
+    def sub_record(fn, *a, **kw):
+        # a sub-record that fails must not cost the headline line: at one GPU the error is
+        # recorded in its place.  Under torchrun a rank that left a sub-record early would be
+        # out of step with the others' collectives, so there the error propagates.
+        if world > 1:
+            return fn(*a, **kw)
+        try:
+            return fn(*a, **kw)
+        except Exception as e:              # noqa: BLE001 (reported, not swallowed)
+            sys.stderr.write("bench.py: sub-record failed: %r\n" % (e,))
+            return {"error": "%s: %s" % (type(e).__name__, e)}
+
     if args.workload == "A" and not args.main_only:
         for key in ("C3", "B", "C5"):
-            subs[key] = bench_projection(env, key, full=False)
+            subs[key] = sub_record(bench_projection, env, key, full=False)
         if not args.no_train:
             try:
                 from pytorch_unsup_pc_b200 import train_step
-                subs["train3"] = train_step.bench(env, args)
             except ImportError:
-                pass
-    env.fence()
+                train_step = None
+            if train_step is not None:
+                subs["train3"] = sub_record(train_step.bench, env, args)
+    try:
+        env.fence()
+    except Exception:                       # noqa: BLE001
+        if world > 1 or not any("error" in r for r in subs.values()):
+            raise                           # only a failed sub-record may leave the device unusable
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
