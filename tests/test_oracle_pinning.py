@@ -90,6 +90,63 @@ def test_oracle_matches_live_reference():
         assert torch.equal(ref[k], orc[k]), k
 
 
+def _sweep_draw(i):
+    """Draw i of a seeded sweep over the argument space of the path (the reference runs each)."""
+    g = torch.Generator().manual_seed(9100 + i)
+    pick = lambda xs: xs[int(torch.randint(len(xs), (1,), generator=g))]   # noqa: E731
+    v = pick([16, 32, 32, 64])
+    spec = dict(V=v, Vz=pick([-1, -1, v // 2]) if i % 3 == 2 else -1, K=pick([1, 3, 5, 11, 21]),
+                sigma=pick([0.2, 0.5, 1.0, 2.0, 3.0]), P=pick([1, 2, 3]), N=pick([1, 17, 300, 900]),
+                kind=pick(["uniform", "clustered", "recipe"]), translation=bool(pick([0, 1])),
+                focal=bool(pick([0, 1])), scale=bool(pick([0, 1, 1])), blur=bool(pick([0, 1, 1, 1])),
+                logsum=bool(pick([0, 1, 1, 1])))
+    if spec["Vz"] != -1:
+        spec["blur"] = False        # the reference's anisotropic kernel raises (gauss_kernel.py:49)
+    return spec
+
+
+@pytest.mark.skipif(not RL.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("i", range(16))
+def test_oracle_matches_live_reference_sweep(i):
+    """The pin of `closed_form` widened from one configuration to a seeded sweep: grid 16^3 / 32^3 /
+    64^3 and anisotropic depth, 1-21 taps over the sigma schedule, clouds of 1-900 points incl.
+    out-of-frustum and piled-up ones (unscreened), every optional input on and off, both DRC
+    forms.  Forward: every output `torch.equal` to the reference executed live; gradients (the
+    reference's own autograd against autograd over the restatement): fp32 rounding of the leaves."""
+    sp = _sweep_draw(i)
+    cfg = default_cfg(vox_size=sp["V"], vox_size_z=sp["Vz"], pc_gauss_kernel_size=sp["K"],
+                      drc_logsum=sp["logsum"])
+    case = _inputs.make_case(cfg, sp["P"], sp["N"], 9200 + i, kind=sp["kind"], translation=sp["translation"],
+                             focal=sp["focal"], scale=sp["scale"], screened=False)
+    # the reference raises on a coordinate of exactly +0.5 (point_cloud_to.py:59); clamped clouds hit it
+    if sp["kind"] == "clustered":
+        case["points"] = case["points"].clamp(-0.499, 0.499)
+    keys = [k for k in ("points", "quat", "translation", "focal", "scale") if case[k] is not None]
+    vz = sp["V"] if sp["Vz"] == -1 else sp["Vz"]
+    Wp, Wd = _inputs.loss_weights(sp["P"], sp["V"])
+    res = []
+    for which in ("reference", "oracle"):
+        lv = {k: case[k].clone().requires_grad_() for k in keys}
+        if which == "reference":
+            kern = RL.ref_smoothing_kernel(cfg, sp["sigma"]) if sp["blur"] else None
+            out = RL.ref_project(cfg, lv["points"], lv["quat"], lv.get("translation"), kern,
+                                 lv.get("scale"), lv.get("focal"))
+        else:
+            kern = CF.smoothing_taps(cfg, sp["sigma"]) if sp["blur"] else None
+            out = CF.project(cfg, lv["points"], lv["quat"], lv.get("translation"), kern,
+                             lv.get("scale"), lv.get("focal"))
+        assert out["voxels"].shape == (sp["P"], vz, sp["V"], sp["V"], 1)
+        loss = (out["proj"] * Wp.double()).sum() + 0.1 * (out["proj_depth"] * Wd.double()).sum()
+        res.append((out, torch.autograd.grad(loss, [lv[k] for k in keys], allow_unused=True)))
+    (ref, gref), (orc, gorc) = res
+    for k in ("proj", "proj_depth", "tr_pc", "voxels", "drc_probs", "voxels_raw"):
+        assert torch.equal(ref[k], orc[k]), (sp, k)
+    for k, a, b in zip(keys, gref, gorc):
+        assert (a is None) == (b is None), (sp, k)
+        if a is not None and float(a.abs().max()) > 0:
+            assert _golden.rel_err(b, a) < 5e-6, (sp, k)
+
+
 MIRRORED = {
     "pc_to": ["pointcloud_project_fast", "pc_perspective_transform", "pointcloud2voxels3d_fast",
               "smoothen_voxels3d", "convolve_rgb", "pc_point_dropout"],
