@@ -57,6 +57,32 @@ def test_oracle_matches_live_reference():
     assert torch.equal(torch.autograd.grad(t_ref, a)[0], torch.autograd.grad(t_or, b)[0])
 
 
+@pytest.mark.skipif(not RL.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("i", range(10))
+def test_oracle_matches_live_reference_sweep(i):
+    """The pin widened to a seeded sweep: 2-5 candidates, 1-6 views, pooled and un-pooled ground
+    truth, per-sample weights, fp32 and fp64 predictions, exact ties between candidates (the
+    argmin must take the FIRST minimum, as torch.argmin does).  Loss, argmin and gradient are
+    bit-identical to the reference's own methods."""
+    g = torch.Generator().manual_seed(7300 + i)
+    pick = lambda xs: xs[int(torch.randint(len(xs), (1,), generator=g))]   # noqa: E731
+    C, BV, V = pick([2, 3, 4, 5]), pick([1, 2, 3, 6]), pick([16, 32, 64])
+    G = V * pick([1, 2, 4])
+    weighted, dtype, scale = pick([False, True]), pick([torch.float32, torch.float64]), pick([1.0, 0.37, 160.0])
+    cfg = RL.reference_cfg(pose_predict_num_candidates=C, pose_predictor_student=False,
+                           variable_num_views=weighted, vox_size=V)
+    masks = (torch.rand(BV, 1, G, G, generator=g) > 0.5).float()
+    projs = torch.rand(BV * C, V, V, 1, generator=g, dtype=dtype)
+    if i % 2:                                   # candidates 0 and C-1 of the first view tie exactly
+        projs[C - 1] = projs[0]
+    w = torch.rand(BV, generator=g).round() if weighted else None
+    a, b = projs.clone().requires_grad_(), projs.clone().requires_grad_()
+    t_ref, m_ref = RL.ref_candidate_loss(cfg, masks.clone(), a, scale, w)
+    t_or, m_or = OL.add_proj_loss(masks, b, C, scale, w)
+    assert t_ref.item() == t_or.item() and m_ref.tolist() == m_or.tolist()
+    assert torch.equal(torch.autograd.grad(t_ref, a)[0], torch.autograd.grad(t_or, b)[0])
+
+
 def test_unsupported_branches_raise():
     import pytorch_unsup_pc_b200 as dpc
     z = {"masks": torch.zeros(2, 1, 8, 8)}

@@ -251,3 +251,51 @@ def test_oracle_composition_matches_live_reference():
     assert t_ref.item() == t_or.item() and m_ref.tolist() == m_or.tolist()
     for x, y in zip(g_or, g_ref):
         assert _golden.rel_err(x, y) < 2e-6
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(),
+                    reason="reference tree not mounted")
+@pytest.mark.parametrize("i", range(8))
+def test_oracle_composition_matches_live_reference_sweep(i):
+    """The same pin over a seeded sweep of what the fused step takes: 1-3 clouds, 1-3 views, 2-4
+    candidates, 32^3 / 64^3, pooled and un-pooled masks, with and without point dropout,
+    translation, focal length, per-sample weights and a loss scale.  Loss and argmin bit-identical
+    to the reference's own functions, gradients to the fp32 rounding of the leaves."""
+    import _inputs
+    from oracle import ref_loader as RL
+    g = torch.Generator().manual_seed(8800 + i)
+    pick = lambda xs: xs[int(torch.randint(len(xs), (1,), generator=g))]   # noqa: E731
+    B, views, C, N, V = pick([1, 2, 3]), pick([1, 2, 3]), pick([2, 3, 4]), pick([60, 250, 500]), pick([32, 32, 64])
+    K, sigma, keep = pick([5, 11, 21]), pick([0.5, 1.5, 3.0]), pick([1.0, 0.75, 0.3])
+    G, scale_w, weighted = V * pick([1, 2]), pick([1.0, 160.0]), pick([False, True])
+    tr, fo = pick([False, True]), pick([False, True])
+    cfg = default_cfg(vox_size=V, pc_gauss_kernel_size=K, pose_predict_num_candidates=C,
+                      variable_num_views=weighted)
+    P = B * views * C
+    case = _inputs.make_case(cfg, P, N, 8900 + i, scale=True, translation=tr, focal=fo, screened=False)
+    cloud = case["points"][:B].contiguous()
+    masks = (torch.rand(B * views, 1, G, G, generator=g) > 0.5).float()
+    w = torch.rand(B * views, generator=g).round() if weighted else None
+    kernel = RL.ref_smoothing_kernel(cfg, sigma)
+    rcfg = RL.reference_cfg(pose_predict_num_candidates=C, pose_predictor_student=False, vox_size=V,
+                            pc_gauss_kernel_size=K, variable_num_views=weighted)
+    names = ["points", "quat", "scale"] + (["translation"] if tr else []) + (["focal"] if fo else [])
+    src = dict(case, points=cloud)
+    res = []
+    for which in ("reference", "oracle"):
+        lv = {k: src[k].clone().requires_grad_() for k in names}
+        if which == "reference":
+            out, idx = RL.ref_project_replicated(rcfg, lv["points"], lv["quat"], views, C, keep, 40 + i,
+                                                 lv.get("translation"), kernel, lv["scale"], lv.get("focal"))
+            total, mins = RL.ref_candidate_loss(rcfg, masks.clone(), out["proj"], scale_w, w)
+        else:
+            total, mins, _ = ORL.project_candidates_loss(
+                cfg, lv["points"], lv["quat"], masks, C, kernel, lv["scale"], lv.get("translation"),
+                lv.get("focal"), scale_w, w, indices=None if idx is None else _pairs(idx))
+        res.append((total, mins, torch.autograd.grad(total, [lv[k] for k in names], allow_unused=True)))
+    (t_ref, m_ref, g_ref), (t_or, m_or, g_or) = res
+    assert t_ref.item() == t_or.item() and m_ref.tolist() == m_or.tolist()
+    for k, x, y in zip(names, g_or, g_ref):
+        assert (x is None) == (y is None), k
+        if y is not None and float(y.abs().max()) > 0:
+            assert _golden.rel_err(x, y) < 5e-6, k
