@@ -27,6 +27,34 @@ def test_oracle_matches_reference_golden():
     assert (idx[:50] == np.arange(100, 150)).all() and (dist[:50] == 0).all()   # first of the duplicates
 
 
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(),
+                    reason="reference tree not mounted")
+@pytest.mark.parametrize("i", range(6))
+def test_oracle_matches_live_reference_sweep(i):
+    """The numpy oracle against the reference's own point_cloud_distance executed live
+    (util/point_cloud_distance.py:25-40) over ragged sizes, clustered clouds, exact duplicates
+    and lattice points (many exactly tied distances: the FIRST minimum must win): idx and proj
+    equal, minDist within 1 ulp (torch's vectorised CPU sqrt against the correctly rounded one)."""
+    from oracle import ref_loader as RL
+    g = torch.Generator().manual_seed(6100 + i)
+    N, M = [(1, 1), (7, 300), (257, 129), (600, 1000), (64, 64), (300, 513)][i]
+    Vs = torch.rand(N, 3, generator=g) - 0.5
+    Vt = torch.rand(M, 3, generator=g) - 0.5
+    if i == 3:                                   # duplicates among the targets and exact hits
+        Vt[500:600] = Vt[100:200]
+        Vs[:40] = Vt[100:140]
+    if i == 4:                                   # a lattice: every source has several equidistant targets
+        Vs = torch.round(Vs * 4) / 4
+        Vt = torch.round(Vt * 4) / 4
+    if i == 5:
+        Vs, Vt = Vs * 0.05, Vt * 0.05 + 0.3     # far, tight clusters: near-ties after rounding
+    r_proj, r_dist, r_idx = RL.ref_point_cloud_distance(Vs, Vt)
+    proj, dist, idx = OC.point_cloud_distance(Vs.numpy(), Vt.numpy())
+    assert np.array_equal(idx, r_idx.numpy())
+    assert np.array_equal(proj, r_proj.numpy())
+    assert _ulp_diff(dist, r_dist.numpy().astype(np.float32)).max() <= 1
+
+
 @pytest.mark.gpu
 def test_cuda_is_bit_exact_against_the_oracle():
     import pytorch_unsup_pc_b200 as dpc
