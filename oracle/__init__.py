@@ -21,6 +21,18 @@ Contents
                  be generated (``tests/golden/make_golden.py``).
 ``config``       the handful of config keys the path reads, with the
                  reference's defaults.
+``loss`` ``replicas`` ``render_loss`` ``chamfer``
+                 restatements of the next rows (candidate-selection
+                 loss, tf_repeat_0 + point dropout, their composition with the
+                 projection, the Chamfer nearest neighbour), each pinned bit for bit
+                 against the reference's own functions executed live (seeded sweeps
+                 in tests/) and by reference-made golden vectors.
+``rgb``          restatement of the point-feature branch from the reference's
+                 TensorFlow original (its torch port does not run), pinned against
+                 that TF source executed unmodified through ``tf_shim``.
+``tf_shim``      a minimal ``tensorflow`` namespace over torch (the ~25 TF-1 ops
+                 util/point_cloud.py calls), validated bit for bit against the
+                 reference's torch port on the occupancy path.
 
 Parity status: the reference ships no golden vectors (SURVEY.md section 8c);
 the oracle is pinned by executing the reference itself in the build container
