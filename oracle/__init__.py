@@ -24,9 +24,11 @@ Contents
 ``loss`` ``replicas`` ``render_loss`` ``chamfer``
                  restatements of the next rows (candidate-selection
                  loss, tf_repeat_0 + point dropout, their composition with the
-                 projection, the Chamfer nearest neighbour), each pinned bit for bit
-                 against the reference's own functions executed live (seeded sweeps
-                 in tests/) and by reference-made golden vectors.
+                 projection, the Chamfer nearest neighbour), each pinned against the
+                 reference's own functions executed live (loss, argmin, indices and
+                 forward values bit for bit; Chamfer distances to 1 ulp of torch's
+                 CPU sqrt; seeded sweeps in tests/) and by reference-made golden
+                 vectors.
 ``rgb``          restatement of the point-feature branch from the reference's
                  TensorFlow original (its torch port does not run), pinned against
                  that TF source executed unmodified through ``tf_shim``.
