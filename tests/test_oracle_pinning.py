@@ -90,6 +90,26 @@ def test_oracle_matches_live_reference():
         assert torch.equal(ref[k], orc[k]), k
 
 
+@pytest.mark.skipif(not RL.available(), reason="reference tree not mounted")
+def test_host_taps_equal_live_reference_over_the_sigma_schedule():
+    """The taps are an input of the path: the product's host mirror (and the oracle's) must hand
+    the kernels the reference's exact fp32 weights at every sigma of the 3.0 -> 0.2 schedule
+    (model_pc_to.py:59-63), for every odd kernel size up to 21."""
+    import pytorch_unsup_pc_b200 as dpc
+    for K in (1, 3, 5, 11, 15, 21):
+        cfg = default_cfg(vox_size=64, pc_gauss_kernel_size=K)
+        for step in range(0, 61):
+            sigma = 3.0 + (0.2 - 3.0) * step / 60.0
+            ref = RL.ref_smoothing_kernel(cfg, sigma)
+            mine = dpc.smoothing_kernel(cfg, sigma)
+            orc = CF.smoothing_taps(cfg, sigma)
+            assert len(ref) == len(mine) == len(orc) == 3
+            for r, m, o in zip(ref, mine, orc):
+                assert r.dtype == m.dtype == torch.float32 and r.shape == m.shape
+                assert torch.equal(r, m) and torch.equal(r, o), (K, sigma)
+            assert torch.equal(dpc.gauss_kernel_1d(K, sigma), RL.load()["gauss_kernel"].gauss_kernel_1d(K, sigma))
+
+
 def _sweep_draw(i):
     """Draw i of a seeded sweep over the argument space of the path (the reference runs each)."""
     g = torch.Generator().manual_seed(9100 + i)
